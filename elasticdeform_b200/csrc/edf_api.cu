@@ -1,0 +1,297 @@
+// edf_api.cu -- C-ABI entry points (include/edf_b200.h) of the B200-native
+// elastic-deformation hot path: validation mirroring the reference's
+// Py_DeformGrid_helper (_deform_grid.c:94-293), descriptor flattening, kernel
+// selection and launch.  sm_100a only; no CPU fallback.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+#include <math.h>
+
+#include "edf_core.h"
+#include "edf_spline_lines.h"
+#include "edf_host.h"
+#include "edf_fast.cuh"
+
+// ----------------------------------------------------------------------------
+// error plumbing
+// ----------------------------------------------------------------------------
+static thread_local const char* g_last_kernel = "none";
+static std::atomic<uint64_t> g_launches{0};
+
+extern "C" const char* edf_last_error(void) { return g_err; }
+extern "C" const char* edf_last_kernel(void) { return g_last_kernel; }
+extern "C" uint64_t edf_launch_count(void) { return g_launches.load(); }
+extern "C" int edf_version(void) { return 100; /* 0.1.0 */ }
+
+extern "C" int edf_device_ok(void)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return major >= 10 ? 1 : 0;
+}
+
+static int check_launch(const char* what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return edf_fail(EDF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    g_launches.fetch_add(1);
+    return EDF_OK;
+}
+
+// ----------------------------------------------------------------------------
+// generic kernels (any naxis<=4 / order / dtype / strides / mode)
+// ----------------------------------------------------------------------------
+template <int NAXIS>
+__global__ void __launch_bounds__(128)
+edf_generic_kernel(const __grid_constant__ EdfParams p)
+{
+    const int64_t kk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (kk < p.size) edf_generic_voxel<NAXIS>(p, kk);
+}
+
+static int launch_generic(const EdfParams& p, cudaStream_t st)
+{
+    if (p.size == 0) return EDF_OK;
+    const int threads = 128;
+    const int64_t blocks = (p.size + threads - 1) / threads;
+    if (blocks > 0x7fffffffLL) return edf_fail(EDF_ERR_RUNTIME, "output too large");
+    switch (p.naxis) {
+    case 1: edf_generic_kernel<1><<<(unsigned)blocks, threads, 0, st>>>(p); break;
+    case 2: edf_generic_kernel<2><<<(unsigned)blocks, threads, 0, st>>>(p); break;
+    case 3: edf_generic_kernel<3><<<(unsigned)blocks, threads, 0, st>>>(p); break;
+    case 4: edf_generic_kernel<4><<<(unsigned)blocks, threads, 0, st>>>(p); break;
+    default: return edf_fail(EDF_ERR_RUNTIME, "unsupported number of deformed axes");
+    }
+    g_last_kernel = p.gradient ? "generic_grad" : "generic";
+    return check_launch("edf_generic_kernel");
+}
+
+static int run_problem(const edf_problem* pr, int gradient, cudaStream_t st)
+{
+    if (!edf_device_ok())
+        return edf_fail(EDF_ERR_CUDA, "no sm_100 (B200) CUDA device available; there is no CPU fallback");
+    EdfParams p;
+    int rc = flatten_problem(pr, gradient, p);
+    if (rc != EDF_OK) return rc;
+    if (p.size == 0) return EDF_OK;
+    if (!(pr->flags & EDF_FLAG_FORCE_GENERIC)) {
+        const char* name = nullptr;
+        uint32_t handled = 0;
+        rc = edf_fast_try_launch(p, st, &name, &handled);
+        if (rc < 0) return edf_fail(EDF_ERR_CUDA, "fast kernel launch failed: %s",
+                                    cudaGetErrorString(g_fast_launch_error));
+        if (rc > 0) {
+            g_last_kernel = name;
+            g_launches.fetch_add((uint64_t)rc);
+            // inputs no specialised kernel took go through the generic kernel
+            int n = 0;
+            for (int i = 0; i < p.ninputs; ++i)
+                if (!((handled >> i) & 1u)) {
+                    if (n != i) p.inp[n] = p.inp[i];
+                    ++n;
+                }
+            if (n == 0) return EDF_OK;
+            p.ninputs = n;
+            rc = launch_generic(p, st);
+            if (rc == EDF_OK) g_last_kernel = "fast+generic";
+            return rc;
+        }
+    }
+    return launch_generic(p, st);
+}
+
+extern "C" int edf_deform_grid(const edf_problem* problem, void* stream)
+{
+    return run_problem(problem, 0, (cudaStream_t)stream);
+}
+
+extern "C" int edf_deform_grid_grad(const edf_problem* problem, void* stream)
+{
+    return run_problem(problem, 1, (cudaStream_t)stream);
+}
+
+extern "C" int edf_deform_grid_batch(const edf_problem* problems, int32_t n, int32_t gradient,
+                                     void* stream)
+{
+    if (n < 0 || (n > 0 && !problems)) return edf_fail(EDF_ERR_RUNTIME, "invalid batch");
+    for (int i = 0; i < n; ++i) {
+        int rc = run_problem(&problems[i], gradient ? 1 : 0, (cudaStream_t)stream);
+        if (rc != EDF_OK) return rc;
+    }
+    return EDF_OK;
+}
+
+// ----------------------------------------------------------------------------
+// K3 / K4: line filters.  A CTA stages `lines_per_block` lines as doubles in
+// shared memory (coalesced in either orientation), one thread then runs the
+// strictly sequential recursion per line, and the CTA writes the lines back.
+// ----------------------------------------------------------------------------
+struct EdfLineParams {
+    const char* in;
+    char* out;
+    int32_t in_dtype, out_dtype;
+    int64_t n;                         // line length
+    int64_t in_lstr, out_lstr;         // byte stride along the line
+    int32_t nother, adjoint;
+    int64_t odim[EDF_MAX_DIMS], in_ostr[EDF_MAX_DIMS], out_ostr[EDF_MAX_DIMS];
+    int64_t nlines;
+    int32_t lines_per_block, ld;       // ld = padded line pitch in doubles (odd)
+    int32_t line_fastest, pad_;        // 1: flattened copy runs along the line first
+    EdfLineFilter f;
+};
+
+__global__ void __launch_bounds__(256)
+edf_line_filter_kernel(const __grid_constant__ EdfLineParams p)
+{
+    extern __shared__ double sbuf[];
+    const int L = p.lines_per_block;
+    int64_t* in_off = (int64_t*)(sbuf + (size_t)L * p.ld);
+    int64_t* out_off = in_off + L;
+    const int64_t line0 = (int64_t)blockIdx.x * L;
+    const int nl = (int)min((int64_t)L, p.nlines - line0);
+
+    for (int l = threadIdx.x; l < nl; l += blockDim.x) {
+        int64_t r = line0 + l, io = 0, oo = 0;
+        for (int q = p.nother - 1; q >= 0; --q) {
+            const int64_t c = r % p.odim[q];
+            r /= p.odim[q];
+            io += c * p.in_ostr[q];
+            oo += c * p.out_ostr[q];
+        }
+        in_off[l] = io;
+        out_off[l] = oo;
+    }
+    __syncthreads();
+
+    const int64_t total = (int64_t)nl * p.n;
+    for (int64_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        int l; int64_t i;
+        if (p.line_fastest) { l = (int)(idx / p.n); i = idx % p.n; }
+        else                { i = idx / nl;        l = (int)(idx % nl); }
+        sbuf[(size_t)l * p.ld + i] = edf_load(p.in + in_off[l] + i * p.in_lstr, p.in_dtype);
+    }
+    __syncthreads();
+
+    for (int l = threadIdx.x; l < nl; l += blockDim.x) {
+        double* c = sbuf + (size_t)l * p.ld;
+        if (p.adjoint) edf_prefilter_adjoint_line(c, p.n, p.f);
+        else           edf_prefilter_line(c, p.n, p.f);
+    }
+    __syncthreads();
+
+    for (int64_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        int l; int64_t i;
+        if (p.line_fastest) { l = (int)(idx / p.n); i = idx % p.n; }
+        else                { i = idx / nl;        l = (int)(idx % nl); }
+        edf_store_cast(p.out + out_off[l] + i * p.out_lstr, p.out_dtype, sbuf[(size_t)l * p.ld + i]);
+    }
+}
+
+static int run_line_filter(const edf_array* input, const edf_array* output, int axis, int order,
+                           int adjoint, cudaStream_t st)
+{
+    if (!edf_device_ok())
+        return edf_fail(EDF_ERR_CUDA, "no sm_100 (B200) CUDA device available; there is no CPU fallback");
+    if (!input || !output) return edf_fail(EDF_ERR_RUNTIME, "null array");
+    if (order < 0 || order > 5)
+        return edf_fail(EDF_ERR_RUNTIME, "spline order not supported");        // _deform_grid.c:71
+    const int nd = input->ndim;
+    if (nd < 0 || nd > EDF_MAX_DIMS || output->ndim != nd)
+        return edf_fail(EDF_ERR_RUNTIME, "input and output dimensions should match");
+    if (axis < 0) axis += nd;                                                  // _deform_grid.c:75
+    if (axis < 0 || axis >= nd) return edf_fail(EDF_ERR_RUNTIME, "invalid axis");
+    if (!dtype_size(input->dtype) || !dtype_size(output->dtype))
+        return edf_fail(EDF_ERR_RUNTIME, "data type not supported");
+    EdfLineParams p;
+    memset(&p, 0, sizeof(p));
+    int64_t total = 1;
+    for (int d = 0; d < nd; ++d) {
+        if (input->shape[d] != output->shape[d])
+            return edf_fail(EDF_ERR_RUNTIME, "input and output shapes should match");
+        total *= input->shape[d];
+    }
+    if (total == 0) return EDF_OK;
+    if (!input->data || !output->data) return edf_fail(EDF_ERR_VALUE, "null data pointer");
+    p.in = (const char*)input->data;
+    p.out = (char*)output->data;
+    p.in_dtype = input->dtype;
+    p.out_dtype = output->dtype;
+    p.n = input->shape[axis];
+    p.in_lstr = input->strides[axis];
+    p.out_lstr = output->strides[axis];
+    p.adjoint = adjoint;
+    p.nlines = 1;
+    int q = 0;
+    int64_t min_other_stride = INT64_MAX;
+    for (int d = 0; d < nd; ++d) {
+        if (d == axis) continue;
+        p.odim[q] = input->shape[d];
+        p.in_ostr[q] = input->strides[d];
+        p.out_ostr[q] = output->strides[d];
+        p.nlines *= input->shape[d];
+        if (input->shape[d] > 1) {
+            int64_t s = input->strides[d] < 0 ? -input->strides[d] : input->strides[d];
+            if (s < min_other_stride) min_other_stride = s;
+        }
+        ++q;
+    }
+    p.nother = q;
+    {
+        int64_t ls = p.in_lstr < 0 ? -p.in_lstr : p.in_lstr;
+        p.line_fastest = (ls <= min_other_stride) ? 1 : 0;
+    }
+    setup_filter(p.f, (order < 2) ? 0 : order, p.n, adjoint);
+    if (order < 2) { p.f.npoles = 0; p.f.gain = 1.0; }     // orders 0/1: plain copy
+    if (order < 2 && adjoint) p.f.gain = 1.0;
+
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int64_t ld = p.n + 1 + (p.n & 1);                // odd pitch: conflict-free 64-bit columns
+    const int64_t per_line = ld * 8 + 16;
+    int64_t L = ((int64_t)max_smem - 1024) / per_line;
+    if (L < 1)
+        return edf_fail(EDF_ERR_MEMORY, "line of %lld elements does not fit in shared memory",
+                        (long long)p.n);
+    // keep >= ~4 CTAs per SM worth of lines when the problem is large enough
+    int64_t Lcap = 64;
+    if (L > Lcap) L = Lcap;
+    if (L > p.nlines) L = p.nlines;
+    p.lines_per_block = (int)L;
+    p.ld = (int)ld;
+    const size_t smem = (size_t)(L * per_line);
+    const int64_t blocks = (p.nlines + L - 1) / L;
+    if (blocks > 0x7fffffffLL) return edf_fail(EDF_ERR_RUNTIME, "too many lines");
+    static thread_local int configured_smem = 0;
+    if ((int)smem > configured_smem) {
+        if (cudaFuncSetAttribute(edf_line_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 max_smem) != cudaSuccess)
+            return edf_fail(EDF_ERR_CUDA, "cudaFuncSetAttribute: %s",
+                            cudaGetErrorString(cudaGetLastError()));
+        configured_smem = max_smem;
+    }
+    int threads = 256;
+    edf_line_filter_kernel<<<(unsigned)blocks, threads, smem, st>>>(p);
+    return check_launch(adjoint ? "edf_line_filter_kernel(adjoint)" : "edf_line_filter_kernel");
+}
+
+extern "C" int edf_spline_filter1d(const edf_array* input, const edf_array* output, int32_t axis,
+                                   int32_t order, void* stream)
+{
+    return run_line_filter(input, output, axis, order, 0, (cudaStream_t)stream);
+}
+
+extern "C" int edf_spline_filter1d_grad(const edf_array* input, const edf_array* output,
+                                        int32_t axis, int32_t order, void* stream)
+{
+    return run_line_filter(input, output, axis, order, 1, (cudaStream_t)stream);
+}

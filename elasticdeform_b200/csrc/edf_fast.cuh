@@ -1,0 +1,516 @@
+// edf_fast.cuh -- specialised sm_100a kernels for the hot configurations
+// (2-D / 3-D deformations of float32 volumes at spline orders 0..5, and order-0
+// "label" volumes of any 1/2/4/8-byte type), forward gather and gradient scatter.
+//
+// Work decomposition: a CTA of 256 threads owns a tile of 64 (x) x 8 (rows) x 4
+// (slabs) output voxels.  The coarse-grid B-spline displacement is contracted
+// separably per tile (edf_fast_core.h) so a voxel needs only 4*naxis fp64 FMAs; all
+// discrete decisions are kept bit-identical to the reference by re-evaluating the
+// rare voxels that sit within 2e-8 of a rounding / boundary threshold in the exact
+// reference order.  Interpolation weights and the (order+1)^naxis-tap gather run in
+// fp32 (float32 data); label copies move raw bits.
+#pragma once
+#include <cuda_runtime.h>
+#include "edf_core.h"
+#include "edf_fast_core.h"
+
+#define EDF_FAST_G 4               // thread groups (slabs in 3-D, row blocks in 2-D)
+#define EDF_FAST_M 8               // rows per group
+#define EDF_FAST_THREADS (EDF_FAST_TX * EDF_FAST_G)
+
+struct EdfFastLaunch {
+    uint32_t input_mask;           // which p.inp[] entries this launch processes
+    uint32_t pad_;
+    uint64_t cval_bits[EDF_MAX_INPUTS];   // constant value converted to the output dtype
+    int32_t  istr_e[EDF_MAX_INPUTS][EDF_MAX_AXIS];   // element strides (deformed axes)
+    int32_t  ostr_e[EDF_MAX_INPUTS][EDF_MAX_AXIS];
+};
+
+template <int NAXIS>
+struct EdfFastSmem {
+    static constexpr int NROWS = (NAXIS == 3) ? EDF_FAST_M : EDF_FAST_G * EDF_FAST_M;
+    static constexpr int NSLAB = (NAXIS == 3) ? EDF_FAST_G : 1;
+    double wz[EDF_FAST_G][4];
+    double wy[NROWS][4];
+    double wx[EDF_FAST_TX][4];
+    int    sz[EDF_FAST_G];
+    int    sy[NROWS];
+    int    sx[EDF_FAST_TX];
+    double A[NAXIS][NSLAB][EDF_FAST_NC][EDF_FAST_NC];
+    double B[NAXIS][EDF_FAST_G][EDF_FAST_M][EDF_FAST_NC];
+    int    nonzero;
+};
+
+// ---------------------------------------------------------------------------------------
+// tile prologue: per-axis control tables, then the separable contractions A (over z)
+// and B (over y) of the displacement coefficients
+// ---------------------------------------------------------------------------------------
+template <int NAXIS>
+__device__ __forceinline__ void edf_fast_tile_setup(const EdfParams& p, EdfFastSmem<NAXIS>& s,
+                                                    int64_t z0, int64_t y0, int64_t x0)
+{
+    constexpr int AX = NAXIS - 1, AY = NAXIS - 2;
+    constexpr int NROWS = EdfFastSmem<NAXIS>::NROWS;
+    constexpr int NSLAB = EdfFastSmem<NAXIS>::NSLAB;
+    const int tid = threadIdx.x;
+    if (tid == 0) s.nonzero = 0;
+    // 64 + NROWS + G table entries, one thread each
+    if (tid < EDF_FAST_TX) {
+        const int64_t o = min(x0 + tid, p.odim[AX] - 1);
+        edf_fast_ctrl_entry(p, AX, o, s.wx[tid], &s.sx[tid]);
+    } else if (tid < EDF_FAST_TX + NROWS) {
+        const int t = tid - EDF_FAST_TX;
+        const int64_t o = min(y0 + t, p.odim[AY] - 1);
+        edf_fast_ctrl_entry(p, AY, o, s.wy[t], &s.sy[t]);
+    } else if (NAXIS == 3 && tid < EDF_FAST_TX + NROWS + EDF_FAST_G) {
+        const int t = tid - EDF_FAST_TX - NROWS;
+        const int64_t o = min(z0 + t, p.odim[0] - 1);
+        edf_fast_ctrl_entry(p, 0, o, s.wz[t], &s.sz[t]);
+    }
+    __syncthreads();
+    const int sy_min = s.sy[0], sx_min = s.sx[0];
+    bool nz = false;
+    constexpr int NA = NAXIS * NSLAB * EDF_FAST_NC * EDF_FAST_NC;
+    for (int e = tid; e < NA; e += EDF_FAST_THREADS) {
+        const int jx = e % EDF_FAST_NC;
+        const int jy = (e / EDF_FAST_NC) % EDF_FAST_NC;
+        const int t = (e / (EDF_FAST_NC * EDF_FAST_NC)) % NSLAB;
+        const int h = e / (EDF_FAST_NC * EDF_FAST_NC * NSLAB);
+        const int64_t my = edf_mirror_index(sy_min + jy, p.ncp[AY]);
+        const int64_t mx = edf_mirror_index(sx_min + jx, p.ncp[AX]);
+        double a = 0.0;
+        if (NAXIS == 3) {
+            const char* base = p.disp + p.dstr[0] * h + my * p.dstr[2] + mx * p.dstr[3];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t mz = edf_mirror_index(s.sz[t] + i, p.ncp[0]);
+                const double c = edf_load(base + mz * p.dstr[1], p.ddtype);
+                nz |= (c != 0.0);
+                a = fma(c, s.wz[t][i], a);
+            }
+        } else {
+            a = edf_load(p.disp + p.dstr[0] * h + my * p.dstr[1] + mx * p.dstr[2], p.ddtype);
+            nz |= (a != 0.0);
+        }
+        s.A[h][t][jy][jx] = a;
+    }
+    if (nz) s.nonzero = 1;                      // benign race: all writers store 1
+    __syncthreads();
+    constexpr int NB = NAXIS * EDF_FAST_G * EDF_FAST_M * EDF_FAST_NC;
+    for (int e = tid; e < NB; e += EDF_FAST_THREADS) {
+        const int jx = e % EDF_FAST_NC;
+        const int m = (e / EDF_FAST_NC) % EDF_FAST_M;
+        const int g = (e / (EDF_FAST_NC * EDF_FAST_M)) % EDF_FAST_G;
+        const int h = e / (EDF_FAST_NC * EDF_FAST_M * EDF_FAST_G);
+        const int row = (NAXIS == 3) ? m : g * EDF_FAST_M + m;
+        const int t = (NAXIS == 3) ? g : 0;
+        const int r0 = s.sy[row] - sy_min;
+        double b = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b = fma(s.A[h][t][r0 + j][jx], s.wy[row][j], b);
+        s.B[h][g][m][jx] = b;
+    }
+    __syncthreads();
+}
+
+// exact reference-order displacement, kept out of line so that its index tables do not
+// inflate the register footprint of the hot loop (it runs for ~1 voxel in 10^6)
+template <int NAXIS>
+__device__ __noinline__ void edf_displacement_exact_cold(const EdfParams& p, const int64_t* o, double* dd)
+{
+    edf_displacement_exact<NAXIS>(p, o, dd);
+}
+
+// un-mapped source coordinates in[h] of one voxel, with the exact-order re-evaluation
+// of the voxels that sit next to a discontinuity
+template <int NAXIS>
+__device__ __forceinline__ void edf_fast_voxel_coords(const EdfParams& p, const EdfFastSmem<NAXIS>& s,
+                                                      const int64_t* o, int g, int m, int tx,
+                                                      const double* wx, int sxrel, double* in)
+{
+    bool danger = false;
+#pragma unroll
+    for (int h = 0; h < NAXIS; ++h) {
+        double d = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d = fma(s.B[h][g][m][sxrel + k], wx[k], d);
+        in[h] = edf_source_coordinate<NAXIS>(p, o, h, d);
+        danger |= edf_near_half_integer(in[h]);
+    }
+    if (danger && s.nonzero) {
+        double dd[NAXIS];
+        edf_displacement_exact_cold<NAXIS>(p, o, dd);
+#pragma unroll
+        for (int h = 0; h < NAXIS; ++h) in[h] = edf_source_coordinate<NAXIS>(p, o, h, dd[h]);
+    }
+}
+
+// per-axis tap offsets (element units) with the reference's mirror edge mapping
+template <int ORDER>
+__device__ __forceinline__ void edf_fast_tap_offsets(int start, int len, int stride_e, int* off)
+{
+    const bool edge = start < 0 || start + ORDER >= len;
+#pragma unroll
+    for (int l = 0; l <= ORDER; ++l) {
+        int idx = start + l;
+        if (edge) idx = (int)edf_mirror_index(idx, len);
+        off[l] = idx * stride_e;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// float32 kernel: forward gather (GRAD=false) or gradient scatter (GRAD=true)
+// ---------------------------------------------------------------------------------------
+template <int NAXIS, int ORDER, bool GRAD>
+__global__ void __launch_bounds__(EDF_FAST_THREADS)
+edf_fast_f32_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L)
+{
+    __shared__ EdfFastSmem<NAXIS> s;
+    constexpr int AX = NAXIS - 1, AY = NAXIS - 2;
+    constexpr int NT = ORDER + 1;
+    const int64_t x0 = (int64_t)blockIdx.x * EDF_FAST_TX;
+    const int64_t y0 = (int64_t)blockIdx.y * EdfFastSmem<NAXIS>::NROWS;
+    const int64_t z0 = (int64_t)blockIdx.z * EDF_FAST_G;
+    edf_fast_tile_setup<NAXIS>(p, s, z0, y0, x0);
+
+    const int tx = threadIdx.x & (EDF_FAST_TX - 1);
+    const int g = threadIdx.x >> 6;
+    const int64_t x = x0 + tx;
+    if (x >= p.odim[AX]) return;
+    double wx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wx[k] = s.wx[tx][k];
+    const int sxrel = s.sx[tx] - s.sx[0];
+
+    for (int m = 0; m < EDF_FAST_M; ++m) {
+        int64_t o[NAXIS];
+        o[AX] = x;
+        if (NAXIS == 3) {
+            o[0] = z0 + g;
+            o[AY] = y0 + m;
+            if (o[0] >= p.odim[0] || o[AY] >= p.odim[AY]) continue;
+        } else {
+            o[AY] = y0 + g * EDF_FAST_M + m;
+            if (o[AY] >= p.odim[AY]) continue;
+        }
+        double in[NAXIS];
+        edf_fast_voxel_coords<NAXIS>(p, s, o, g, m, tx, wx, sxrel, in);
+
+        for (int ii = 0; ii < p.ninputs; ++ii) {
+            if (!((L.input_mask >> ii) & 1u)) continue;
+            const EdfInputDesc& d = p.inp[ii];
+            bool constant = false;
+            float w[NAXIS][NT];
+            int off[NAXIS][NT];
+#pragma unroll
+            for (int h = 0; h < NAXIS; ++h) {
+                int st = 0;
+                float fr = 0.f;
+                if (!constant && !edf_fast_finish(p, d.mode, ORDER, h, in[h], &st, &fr)) constant = true;
+                if (!constant) {
+                    edf_fast_tap_offsets<ORDER>(st, (int)p.idim[h], L.istr_e[ii][h], off[h]);
+                    if (ORDER > 0) edf_bspline_weights_f32<ORDER>(fr, w[h]);
+                }
+            }
+            int64_t obase = 0;
+#pragma unroll
+            for (int h = 0; h < NAXIS; ++h) obase += o[h] * (int64_t)L.ostr_e[ii][h];
+
+            for (int64_t ss = 0; ss < d.nsteps; ++ss) {
+                int64_t istep = 0, ostep = 0, r = ss;
+                for (int q = 0; q < d.nstep_rank; ++q) {
+                    const int64_t c = r % d.step_dim[q];
+                    r /= d.step_dim[q];
+                    istep += d.in_step_str[q] * c;
+                    ostep += d.out_step_str[q] * c;
+                }
+                float* po = (float*)(d.out + ostep) + obase;
+                if (!GRAD) {
+                    const float* __restrict__ pi = (const float*)(d.in + istep);
+                    float t;
+                    if (constant) {
+                        t = __uint_as_float((uint32_t)L.cval_bits[ii]);
+                    } else if (ORDER == 0) {
+                        int e = 0;
+#pragma unroll
+                        for (int h = 0; h < NAXIS; ++h) e += off[h][0];
+                        t = __ldg(pi + e);
+                    } else if (NAXIS == 3) {
+                        t = 0.f;
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) {
+                            float ti = 0.f;
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) {
+                                const float* row = pi + (off[0][i] + off[1][j]);
+                                float tj = 0.f;
+#pragma unroll
+                                for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + off[2][k]), w[2][k], tj);
+                                ti = fmaf(tj, w[1][j], ti);
+                            }
+                            t = fmaf(ti, w[0][i], t);
+                        }
+                    } else {
+                        t = 0.f;
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            const float* row = pi + off[0][j];
+                            float tj = 0.f;
+#pragma unroll
+                            for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + off[1][k]), w[1][k], tj);
+                            t = fmaf(tj, w[0][j], t);
+                        }
+                    }
+                    *po = t;
+                } else if (!constant) {
+                    float* pi = (float*)(d.in + istep);
+                    const float gval = *po;
+                    if (ORDER == 0) {
+                        int e = 0;
+#pragma unroll
+                        for (int h = 0; h < NAXIS; ++h) e += off[h][0];
+                        atomicAdd(pi + e, gval);
+                    } else if (NAXIS == 3) {
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) {
+                            const float gi = gval * w[0][i];
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) {
+                                const float gj = gi * w[1][j];
+                                float* row = pi + (off[0][i] + off[1][j]);
+#pragma unroll
+                                for (int k = 0; k < NT; ++k) atomicAdd(row + off[2][k], gj * w[2][k]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            const float gj = gval * w[0][j];
+                            float* row = pi + off[0][j];
+#pragma unroll
+                            for (int k = 0; k < NT; ++k) atomicAdd(row + off[1][k], gj * w[1][k]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// order-0 forward for any element type: the output is a bit copy of the selected input
+// voxel (label volumes, BASELINE config 3's int32 input) or the converted cval
+// ---------------------------------------------------------------------------------------
+template <int NAXIS, typename T>
+__global__ void __launch_bounds__(EDF_FAST_THREADS)
+edf_fast_copy_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L)
+{
+    __shared__ EdfFastSmem<NAXIS> s;
+    constexpr int AX = NAXIS - 1, AY = NAXIS - 2;
+    const int64_t x0 = (int64_t)blockIdx.x * EDF_FAST_TX;
+    const int64_t y0 = (int64_t)blockIdx.y * EdfFastSmem<NAXIS>::NROWS;
+    const int64_t z0 = (int64_t)blockIdx.z * EDF_FAST_G;
+    edf_fast_tile_setup<NAXIS>(p, s, z0, y0, x0);
+
+    const int tx = threadIdx.x & (EDF_FAST_TX - 1);
+    const int g = threadIdx.x >> 6;
+    const int64_t x = x0 + tx;
+    if (x >= p.odim[AX]) return;
+    double wx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wx[k] = s.wx[tx][k];
+    const int sxrel = s.sx[tx] - s.sx[0];
+
+    for (int m = 0; m < EDF_FAST_M; ++m) {
+        int64_t o[NAXIS];
+        o[AX] = x;
+        if (NAXIS == 3) {
+            o[0] = z0 + g;
+            o[AY] = y0 + m;
+            if (o[0] >= p.odim[0] || o[AY] >= p.odim[AY]) continue;
+        } else {
+            o[AY] = y0 + g * EDF_FAST_M + m;
+            if (o[AY] >= p.odim[AY]) continue;
+        }
+        double in[NAXIS];
+        edf_fast_voxel_coords<NAXIS>(p, s, o, g, m, tx, wx, sxrel, in);
+
+        for (int ii = 0; ii < p.ninputs; ++ii) {
+            if (!((L.input_mask >> ii) & 1u)) continue;
+            const EdfInputDesc& d = p.inp[ii];
+            bool constant = false;
+            int64_t e = 0;
+#pragma unroll
+            for (int h = 0; h < NAXIS; ++h) {
+                int st = 0, off0;
+                float fr;
+                if (!constant && !edf_fast_finish(p, d.mode, 0, h, in[h], &st, &fr)) constant = true;
+                if (!constant) {
+                    edf_fast_tap_offsets<0>(st, (int)p.idim[h], L.istr_e[ii][h], &off0);
+                    e += off0;
+                }
+            }
+            int64_t obase = 0;
+#pragma unroll
+            for (int h = 0; h < NAXIS; ++h) obase += o[h] * (int64_t)L.ostr_e[ii][h];
+            for (int64_t ss = 0; ss < d.nsteps; ++ss) {
+                int64_t istep = 0, ostep = 0, r = ss;
+                for (int q = 0; q < d.nstep_rank; ++q) {
+                    const int64_t c = r % d.step_dim[q];
+                    r /= d.step_dim[q];
+                    istep += d.in_step_str[q] * c;
+                    ostep += d.out_step_str[q] * c;
+                }
+                T v;
+                if (constant) v = (T)L.cval_bits[ii];
+                else          v = __ldg((const T*)(d.in + istep) + e);
+                *((T*)(d.out + ostep) + obase) = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side selection
+// ---------------------------------------------------------------------------------------
+static thread_local cudaError_t g_fast_launch_error = cudaSuccess;
+
+enum { EDF_CLASS_NONE = 0, EDF_CLASS_F32 = 1, EDF_CLASS_COPY = 2 };
+
+static inline int edf_elem_size(int dt)
+{
+    switch (dt) {
+    case EDF_BOOL: case EDF_U8: case EDF_I8: return 1;
+    case EDF_U16: case EDF_I16: return 2;
+    case EDF_U32: case EDF_I32: case EDF_F32: return 4;
+    default: return 8;
+    }
+}
+
+// class of input ii, or NONE when it has to go through the generic kernel
+static int edf_fast_input_class(const EdfParams& p, int ii, EdfFastLaunch& L)
+{
+    const EdfInputDesc& d = p.inp[ii];
+    if (d.in_dtype != d.out_dtype) return EDF_CLASS_NONE;
+    const int es = edf_elem_size(d.in_dtype);
+    int cls;
+    if (d.in_dtype == EDF_F32) cls = EDF_CLASS_F32;
+    else if (d.order == 0 && !p.gradient && d.in_dtype != EDF_BOOL) cls = EDF_CLASS_COPY;
+    else return EDF_CLASS_NONE;
+    int64_t max_in = 0, max_out = 0;
+    for (int h = 0; h < p.naxis; ++h) {
+        if (d.istr[h] % es || d.ostr[h] % es) return EDF_CLASS_NONE;
+        const int64_t se = d.istr[h] / es, so = d.ostr[h] / es;
+        if (se < 0 || so < 0) return EDF_CLASS_NONE;
+        max_in += se * (p.idim[h] - 1);
+        max_out += so * (p.odim[h] - 1);
+        if (se > 0x7fffffffLL || so > 0x7fffffffLL) return EDF_CLASS_NONE;
+        L.istr_e[ii][h] = (int32_t)se;
+        L.ostr_e[ii][h] = (int32_t)so;
+    }
+    if (max_in > 0x7fffffffLL || max_out > 0x7fffffffLL) return EDF_CLASS_NONE;
+    if (((uintptr_t)d.in % es) || ((uintptr_t)d.out % es)) return EDF_CLASS_NONE;
+    for (int q = 0; q < d.nstep_rank; ++q)
+        if (d.in_step_str[q] % es || d.out_step_str[q] % es) return EDF_CLASS_NONE;
+    uint64_t bits = 0;
+    edf_store((char*)&bits, d.out_dtype, d.cval);       // reference conversion rule (deform.c:906-919)
+    L.cval_bits[ii] = bits;
+    return cls;
+}
+
+template <int NAXIS, bool GRAD>
+static void edf_fast_launch_f32(int order, dim3 grid, cudaStream_t st, const EdfParams& p,
+                                const EdfFastLaunch& L)
+{
+    switch (order) {
+    case 0: edf_fast_f32_kernel<NAXIS, 0, GRAD><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    case 1: edf_fast_f32_kernel<NAXIS, 1, GRAD><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    case 2: edf_fast_f32_kernel<NAXIS, 2, GRAD><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    case 3: edf_fast_f32_kernel<NAXIS, 3, GRAD><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    case 4: edf_fast_f32_kernel<NAXIS, 4, GRAD><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    default: edf_fast_f32_kernel<NAXIS, 5, GRAD><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    }
+}
+
+template <int NAXIS>
+static void edf_fast_launch_copy(int es, dim3 grid, cudaStream_t st, const EdfParams& p,
+                                 const EdfFastLaunch& L)
+{
+    switch (es) {
+    case 1: edf_fast_copy_kernel<NAXIS, uint8_t><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    case 2: edf_fast_copy_kernel<NAXIS, uint16_t><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    case 4: edf_fast_copy_kernel<NAXIS, uint32_t><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    default: edf_fast_copy_kernel<NAXIS, unsigned long long><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    }
+}
+
+// Tries to run (part of) the problem on the specialised kernels.
+//   *handled_mask receives the inputs that were processed (the caller runs the generic
+//   kernel for the others); returns the number of kernels launched, or <0 on a launch error.
+static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char** name,
+                               uint32_t* handled_mask)
+{
+    *handled_mask = 0;
+    if (p.naxis != 2 && p.naxis != 3) return 0;
+    const int AX = p.naxis - 1, AY = p.naxis - 2;
+    for (int a = 0; a < p.naxis; ++a) {
+        if (p.idim[a] < 2 || p.idim[a] > 0x3fffffff || p.odim[a] > 0x3fffffff) return 0;
+        if (p.ncp[a] > 0x3fffffff) return 0;
+    }
+    if (p.ddtype != EDF_F64 && p.ddtype != EDF_F32) return 0;
+    if (!edf_fast_ctrl_span_ok(p, AX, EDF_FAST_TX)) return 0;
+    if (!edf_fast_ctrl_span_ok(p, AY, p.naxis == 3 ? EDF_FAST_M : EDF_FAST_G * EDF_FAST_M)) return 0;
+
+    EdfFastLaunch L;
+    memset(&L, 0, sizeof(L));
+    int cls[EDF_MAX_INPUTS];
+    for (int ii = 0; ii < p.ninputs; ++ii) cls[ii] = edf_fast_input_class(p, ii, L);
+
+    dim3 grid;
+    grid.x = (unsigned)((p.odim[AX] + EDF_FAST_TX - 1) / EDF_FAST_TX);
+    if (p.naxis == 3) {
+        grid.y = (unsigned)((p.odim[AY] + EDF_FAST_M - 1) / EDF_FAST_M);
+        grid.z = (unsigned)((p.odim[0] + EDF_FAST_G - 1) / EDF_FAST_G);
+    } else {
+        grid.y = (unsigned)((p.odim[AY] + EDF_FAST_G * EDF_FAST_M - 1) / (EDF_FAST_G * EDF_FAST_M));
+        grid.z = 1;
+    }
+    if (grid.y > 65535u || grid.z > 65535u) return 0;
+
+    int launches = 0;
+    bool done[EDF_MAX_INPUTS] = {false};
+    for (int ii = 0; ii < p.ninputs; ++ii) {
+        if (done[ii] || cls[ii] == EDF_CLASS_NONE) continue;
+        // group every later input with the same class / order / element size
+        uint32_t mask = 0;
+        const int es = edf_elem_size(p.inp[ii].in_dtype);
+        for (int jj = ii; jj < p.ninputs; ++jj) {
+            if (done[jj] || cls[jj] != cls[ii]) continue;
+            if (p.inp[jj].order != p.inp[ii].order) continue;
+            if (edf_elem_size(p.inp[jj].in_dtype) != es) continue;
+            mask |= 1u << jj;
+            done[jj] = true;
+        }
+        L.input_mask = mask;
+        if (cls[ii] == EDF_CLASS_F32) {
+            const int order = p.inp[ii].order;
+            if (p.naxis == 3) {
+                if (p.gradient) edf_fast_launch_f32<3, true>(order, grid, st, p, L);
+                else            edf_fast_launch_f32<3, false>(order, grid, st, p, L);
+            } else {
+                if (p.gradient) edf_fast_launch_f32<2, true>(order, grid, st, p, L);
+                else            edf_fast_launch_f32<2, false>(order, grid, st, p, L);
+            }
+            *name = p.gradient ? "fast_f32_grad" : "fast_f32";
+        } else {
+            if (p.naxis == 3) edf_fast_launch_copy<3>(es, grid, st, p, L);
+            else              edf_fast_launch_copy<2>(es, grid, st, p, L);
+            *name = "fast_copy";
+        }
+        g_fast_launch_error = cudaGetLastError();
+        if (g_fast_launch_error != cudaSuccess) return -1;
+        ++launches;
+        *handled_mask |= mask;
+    }
+    return launches;
+}

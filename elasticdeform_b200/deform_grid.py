@@ -1,0 +1,565 @@
+"""Host-side mirror of the reference's Python API for the elastic-deformation path.
+
+Same function names, argument meaning, defaults and error behaviour as
+``elasticdeform/deform_grid.py`` of gvtulder/elasticdeform (cited below as
+``ref:LINE``), so that ``import elasticdeform_b200 as elasticdeform`` is a
+drop-in.  What differs is what happens underneath ``ref:174`` / ``ref:274``:
+instead of the CPU loop of ``_deform_grid.c`` the arrays are handed (as device
+pointers) to the C-ABI library ``libedf_b200.so`` whose kernels are sm_100a CUDA.
+The spline prefilter (``scipy.ndimage.spline_filter1d`` in the reference,
+``ref:160``, ``ref:168``, ``ref:271``) and its adjoint (``ref:282``) also run on
+the device, so a default ``prefilter=True`` call never leaves the GPU.
+
+Inputs may be NumPy arrays (copied to the GPU and back, like any accelerator
+plug-in) or torch CUDA tensors (zero copies; the result stays on the device).
+PyTorch is used only for device memory, streams and copies.
+"""
+import ctypes
+import warnings
+
+import numpy
+
+from . import _lib
+
+try:  # torch is plumbing (device memory / streams); required for any compute
+    import torch
+except Exception as _e:  # pragma: no cover
+    torch = None
+    _torch_import_error = _e
+
+
+# --------------------------------------------------------------------------------------
+# device plumbing
+# --------------------------------------------------------------------------------------
+def _require_cuda():
+    if torch is None:
+        raise RuntimeError("elasticdeform_b200 needs PyTorch for device memory: %r" % (_torch_import_error,))
+    if not torch.cuda.is_available():
+        raise RuntimeError("elasticdeform_b200: no CUDA device is available and there is no CPU fallback "
+                           "(the hot path is sm_100a CUDA only).")
+    lib = _lib.load_library()
+    return lib
+
+
+def _is_tensor(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def _np_dtype_of(x):
+    if _is_tensor(x):
+        try:
+            return numpy.dtype(str(x.dtype).replace('torch.', ''))
+        except TypeError:
+            raise RuntimeError('data type not supported')      # ref deform.c:889-893
+    return x.dtype
+
+
+def _torch_dtype(np_dtype):
+    name = numpy.dtype(np_dtype).name
+    if not hasattr(torch, name):
+        raise RuntimeError('data type not supported')
+    return getattr(torch, name)
+
+
+def _device_of(xs):
+    for x in xs:
+        if _is_tensor(x) and x.is_cuda:
+            return x.device
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _to_device(x, device):
+    """numpy array / torch tensor -> torch CUDA tensor (no copy if already there)."""
+    if _is_tensor(x):
+        x = x.detach()
+        return x if x.is_cuda else x.to(device, non_blocking=True)
+    _lib.dtype_code(x.dtype)                                  # raises for unsupported dtypes
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")                   # read-only arrays are only read
+            t = torch.from_numpy(x)
+    except (ValueError, TypeError):
+        t = torch.from_numpy(numpy.ascontiguousarray(x))      # negative strides etc.
+    return t.to(device, non_blocking=True)
+
+
+def _edf_array(t):
+    item = t.element_size()
+    return _lib.make_array(t.data_ptr() if t.numel() else 0, _np_dtype_of(t), tuple(t.shape),
+                           tuple(s * item for s in t.stride()))
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _spline_filter1d_device(lib, src, dst, axis, order, adjoint=False):
+    a_in, a_out = _edf_array(src), _edf_array(dst)
+    fn = lib.edf_spline_filter1d_grad if adjoint else lib.edf_spline_filter1d
+    _lib.check(fn(ctypes.byref(a_in), ctypes.byref(a_out), int(axis), int(order), _stream_ptr(src.device)))
+
+
+def _prefilter_displacement(lib, displacement, device):
+    """ref:166-169 -- order-3 prefilter of the control grid along every grid axis, result kept
+    in the displacement's own dtype after each axis (numpy.zeros_like + output=)."""
+    d = _to_device(displacement, device)
+    d_f = torch.empty_like(d, memory_format=torch.contiguous_format)
+    if d.ndim <= 1:
+        d_f.zero_()
+    src = d
+    for ax in range(1, d.ndim):
+        _spline_filter1d_device(lib, src, d_f, ax, 3)
+        src = d_f
+    if d_f.dtype not in (torch.float64, torch.float32):
+        # the C loop reads integer coefficients through a (double) cast (deform.c:715-741)
+        d_f = d_f.to(torch.float64)
+    return d_f
+
+
+def _launch(lib, gradient, ins, outs, displacement_f, output_offset, axis, order, mode, cval,
+            inverse_affine, flags=0):
+    n = len(ins)
+    naxis = len(axis[0])
+    if n > _lib.EDF_MAX_INPUTS:
+        raise RuntimeError('too many inputs (max %d)' % _lib.EDF_MAX_INPUTS)
+    if naxis > _lib.EDF_MAX_AXIS:
+        raise RuntimeError('too many deformed axes (max %d)' % _lib.EDF_MAX_AXIS)
+    in_arr = (_lib.EdfArray * n)(*[_edf_array(t) for t in ins])
+    out_arr = (_lib.EdfArray * n)(*[_edf_array(t) for t in outs])
+    pr = _lib.EdfProblem()
+    pr.ninputs = n
+    pr.naxis = naxis
+    pr.inputs = in_arr
+    pr.outputs = out_arr
+    pr.displacement = _edf_array(displacement_f)
+    keep = [in_arr, out_arr]
+    if output_offset is not None:
+        off = (ctypes.c_int64 * naxis)(*[int(v) for v in output_offset])
+        pr.output_offset = off
+        keep.append(off)
+    ax = (ctypes.c_int32 * (n * naxis))(*[int(a) for tup in axis for a in tup])
+    od = (ctypes.c_int32 * n)(*[int(o) for o in order])
+    md = (ctypes.c_int32 * n)(*[int(m) for m in mode])
+    cv = (ctypes.c_double * n)(*[float(c) for c in cval])
+    pr.axis, pr.orders, pr.modes, pr.cvals = ax, od, md, cv
+    keep += [ax, od, md, cv]
+    if inverse_affine is not None:
+        flat = numpy.ascontiguousarray(inverse_affine, dtype='float64').ravel()
+        af = (ctypes.c_double * flat.size)(*flat.tolist())
+        pr.affine = af
+        keep.append(af)
+    pr.flags = int(flags)
+    fn = lib.edf_deform_grid_grad if gradient else lib.edf_deform_grid
+    _lib.check(fn(ctypes.byref(pr), _stream_ptr(ins[0].device)))
+
+
+def _from_device(t, like):
+    """Return the result in the same kind of container as the corresponding input."""
+    if _is_tensor(like):
+        return t if like.is_cuda else t.to(like.device)
+    return t.cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------
+# public API (ref:6, ref:52, ref:182)
+# --------------------------------------------------------------------------------------
+def deform_random_grid(X, sigma=25, points=3, order=3, mode='constant', cval=0.0,
+                       crop=None, prefilter=True, axis=None,
+                       affine=None, rotate=None, zoom=None):
+    """
+    Elastic deformation with a random deformation grid (ref:6-49).
+
+    Generates a random, square deformation grid with displacements sampled from a
+    normal distribution with standard deviation `sigma` (from NumPy's global RNG,
+    exactly like ref:48) and applies it with ``deform_grid``.
+
+    Parameters
+    ----------
+    X : numpy array / torch CUDA tensor, or list of them
+        image, or list of images of the same size
+    sigma : float
+        standard deviation of the normal distribution
+    points : int or list of ints
+        number of points of the deformation grid
+
+    See ``deform_grid`` for the other parameters.
+    """
+    Xs = _normalize_inputs(X)
+    axis, deform_shape = _normalize_axis_list(axis, Xs)
+
+    if not isinstance(points, (list, tuple)):
+        points = [points] * len(deform_shape)
+
+    displacement = numpy.random.randn(len(deform_shape), *points) * sigma
+    return deform_grid(X, displacement, order, mode, cval, crop, prefilter, axis, affine, rotate, zoom)
+
+
+def deform_grid(X, displacement, order=3, mode='constant', cval=0.0, crop=None, prefilter=True, axis=None,
+                affine=None, rotate=None, zoom=None, *, _flags=0):
+    """
+    Elastic deformation with a deformation grid (ref:52-179), computed on a B200.
+
+    A coarse displacement grid (one displacement vector per control point) is
+    interpolated with cubic B-splines to a displacement for every output pixel;
+    the input is then sampled at the displaced positions with spline interpolation
+    of the requested order.
+
+    Parameters
+    ----------
+    X : numpy array / torch CUDA tensor, or list of them
+        image, or list of images of the same size. For a list, `order`, `mode`,
+        `cval` may be lists with one value per image.
+    displacement : numpy array (or tensor) of shape (naxis, P_0, ..., P_{naxis-1})
+        displacement vectors for each control point
+    order : {0, 1, 2, 3, 4, 5}
+        interpolation order
+    mode : {'nearest', 'wrap', 'reflect', 'mirror', 'constant'}
+        border mode (the reference's pre-1.6-SciPy semantics, deform.c:47-128)
+    cval : float
+        constant value used if mode == 'constant'
+    crop : None or list of slice()
+        crop the output (simple slices over the deformed axes only)
+    prefilter : bool
+        if True the input is B-spline prefiltered first (orders > 1)
+    axis : None, int, tuple of ints, or list of tuples
+        the axes to deform over (default: all)
+    affine : None or array of shape (ndim, ndim + 1)
+        affine transformation applied to the output
+    rotate, zoom : float or None
+        2-D only: rotate (degrees) / zoom the output around its centre
+
+    Returns
+    -------
+    The deformed image, or a list of deformed images if a list of inputs is given
+    (NumPy in -> NumPy out; CUDA tensor in -> CUDA tensor out).
+    """
+    # prepare inputs and axis selection
+    Xs = _normalize_inputs(X)
+    axis, deform_shape = _normalize_axis_list(axis, Xs)
+
+    # prepare output cropping
+    output_shapes, output_offset = _compute_output_shapes(Xs, axis, deform_shape, crop)
+
+    # prepare other parameters
+    displacement = _normalize_displacement(displacement, Xs, axis)
+    order = _normalize_order(order, Xs)
+    mode = _normalize_mode(mode, Xs)
+    cval = _normalize_cval(cval, Xs)
+    affine = _normalize_affine(affine, axis)
+
+    # compute inverse affine given output affine
+    inverse_affine = _compute_inverse_affine(affine)
+
+    # add rotation and zoom to the inverse affine matrix
+    inverse_affine = _apply_rotation_and_zoom(rotate, zoom, inverse_affine,
+                                              [output_shapes[0][d] for d in axis[0]])
+
+    lib = _require_cuda()
+    device = _device_of(Xs)
+    with torch.cuda.device(device):
+        Xs_d = [_to_device(x, device) for x in Xs]
+
+        # prefilter inputs (ref:155-164): per deformed axis, result rounded to the
+        # array dtype after each axis
+        Xs_f = []
+        for i, x in enumerate(Xs_d):
+            if prefilter and order[i] > 1:
+                x_f = torch.empty_like(x)
+                if len(axis[i]) == 0:
+                    x_f.zero_()
+                src = x
+                for d in axis[i]:
+                    _spline_filter1d_device(lib, src, x_f, d, int(order[i]))
+                    src = x_f
+                Xs_f.append(x_f)
+            else:
+                Xs_f.append(x)
+
+        # prefilter displacement (ref:166-169)
+        displacement_f = _prefilter_displacement(lib, displacement, device)
+
+        # prepare output arrays (ref:172; every element is written by the kernel)
+        outputs = [torch.empty(tuple(os), dtype=x.dtype, device=device) for os, x in zip(output_shapes, Xs_d)]
+
+        _launch(lib, 0, Xs_f, outputs, displacement_f, output_offset, axis, order, mode, cval,
+                inverse_affine, _flags)
+
+        results = [_from_device(o, x) for o, x in zip(outputs, Xs)]
+
+    if isinstance(X, list):
+        return results
+    else:
+        return results[0]
+
+
+def deform_grid_gradient(dY, displacement, order=3, mode='constant', cval=0.0, crop=None,
+                         prefilter=True, axis=None, X_shape=None,
+                         affine=None, rotate=None, zoom=None, *, _flags=0):
+    """
+    Gradient for deform_grid (ref:182-291): the exact adjoint of the forward
+    operation with respect to the input X, including the interpolation (a
+    scatter-add of dY through the same spline weights) and, for orders > 1 with
+    `prefilter`, the adjoint of the prefilter.
+
+    `X_shape` (a tuple, or a list of tuples) is the shape of the original inputs and
+    is required if `crop` is used.  See ``deform_grid`` for the other parameters.
+
+    Returns the gradient with respect to X (same container kind as dY).
+    """
+    # prepare inputs
+    dYs = _normalize_inputs(dY)
+
+    # find input shape
+    if isinstance(X_shape, tuple):
+        X_shape = [X_shape]
+    elif X_shape is None:
+        if crop is not None:
+            raise ValueError("X_shape is required if the crop parameter is given.")
+        X_shape = [dy.shape for dy in dYs]
+
+    # stand-ins for the dX arrays during normalisation (shape / ndim only)
+    dXs_meta = [_ShapeOnly(tuple(s)) for s in X_shape]
+
+    # prepare axis selection
+    axis, deform_shape = _normalize_axis_list(axis, dXs_meta)
+
+    # prepare cropping
+    output_shapes, output_offset = _compute_output_shapes(dXs_meta, axis, deform_shape, crop)
+    if [tuple(s) for s in output_shapes] != [tuple(dy.shape) for dy in dYs]:
+        raise ValueError("X_shape does not match output shape and cropping. "
+                         "Expected output shape is %s, but %s given."
+                         % (str(output_shapes), str([tuple(dy.shape) for dy in dYs])))
+
+    # prepare other parameters
+    displacement = _normalize_displacement(displacement, dYs, axis)
+    order = _normalize_order(order, dYs)
+    mode = _normalize_mode(mode, dYs)
+    cval = _normalize_cval(cval, dYs)
+    affine = _normalize_affine(affine, axis)
+
+    # compute inverse affine given output affine
+    inverse_affine = _compute_inverse_affine(affine)
+
+    # add rotation and zoom to the affine matrix
+    inverse_affine = _apply_rotation_and_zoom(rotate, zoom, inverse_affine,
+                                              [output_shapes[0][d] for d in axis[0]])
+
+    lib = _require_cuda()
+    device = _device_of(dYs)
+    with torch.cuda.device(device):
+        dYs_d = [_to_device(dy, device) for dy in dYs]
+
+        # initialize gradient outputs (ref:243) -- the scatter accumulates into zeros
+        dXs = [torch.zeros(tuple(s), dtype=dy.dtype, device=device) for s, dy in zip(X_shape, dYs_d)]
+
+        # prefilter displacement (ref:269-272)
+        displacement_f = _prefilter_displacement(lib, displacement, device)
+
+        _launch(lib, 1, dXs, dYs_d, displacement_f, output_offset, axis, order, mode, cval,
+                inverse_affine, _flags)
+
+        # compute gradient of prefilter operation (ref:277-286)
+        dXs_f = []
+        for i, x in enumerate(dXs):
+            if prefilter and order[i] > 1:
+                x_f = torch.empty_like(x)
+                if len(axis[i]) == 0:
+                    x_f.zero_()
+                src = x
+                for d in axis[i]:
+                    _spline_filter1d_device(lib, src, x_f, d, int(order[i]), adjoint=True)
+                    src = x_f
+                dXs_f.append(x_f)
+            else:
+                dXs_f.append(x)
+
+        results = [_from_device(dx, dy) for dx, dy in zip(dXs_f, dYs)]
+
+    if isinstance(dY, list):
+        return results
+    else:
+        return results[0]
+
+
+# --------------------------------------------------------------------------------------
+# argument normalisation -- behaviour (types, messages) of ref:295-454
+# --------------------------------------------------------------------------------------
+class _ShapeOnly(object):
+    """shape/ndim carrier used where the reference allocates dX before normalising (ref:243-246)."""
+    def __init__(self, shape):
+        self.shape = shape
+        self.ndim = len(shape)
+
+
+def _is_array(x):
+    return isinstance(x, numpy.ndarray) or _is_tensor(x)
+
+
+def _normalize_inputs(X):
+    if _is_array(X):
+        Xs = [X]
+    elif isinstance(X, list):
+        Xs = X
+    else:
+        raise Exception('X should be a numpy.ndarray or a list of numpy.ndarrays.')
+
+    # check X inputs
+    assert len(Xs) > 0, 'You must provide at least one image.'
+    assert all(_is_array(x) for x in Xs), 'All elements of X should be numpy.ndarrays.'
+    return Xs
+
+
+def _normalize_axis_list(axis, Xs):
+    if axis is None:
+        axis = [tuple(range(x.ndim)) for x in Xs]
+    elif isinstance(axis, int):
+        axis = (axis,)
+    if isinstance(axis, tuple):
+        axis = [axis] * len(Xs)
+    assert len(axis) == len(Xs), 'Number of axis tuples should match number of inputs.'
+    input_shapes = []
+    for x, ax in zip(Xs, axis):
+        assert isinstance(ax, tuple), 'axis should be given as a tuple'
+        assert all(isinstance(a, int) for a in ax), 'axis must contain ints'
+        assert len(ax) == len(axis[0]), 'All axis tuples should have the same length.'
+        assert ax == tuple(set(ax)), 'axis must be sorted and unique'
+        assert all(0 <= a < x.ndim for a in ax), 'invalid axis for input'
+        input_shapes.append(tuple(x.shape[d] for d in ax))
+    assert len(set(input_shapes)) == 1, 'All inputs should have the same shape.'
+    deform_shape = input_shapes[0]
+    return axis, deform_shape
+
+
+def _compute_output_shapes(Xs, axis, deform_shape, crop):
+    if crop is not None:
+        assert isinstance(crop, (tuple, list)), "crop must be a tuple or a list."
+        assert len(crop) == len(deform_shape)
+        output_shapes = [list(x.shape) for x in Xs]
+        output_offset = [0 for d in range(len(axis[0]))]
+        for d in range(len(axis[0])):
+            if isinstance(crop[d], slice):
+                assert crop[d].step is None
+                start = (crop[d].start or 0)
+                stop = (crop[d].stop or deform_shape[d])
+                assert start >= 0
+                assert start < stop and stop <= deform_shape[d]
+                for i in range(len(Xs)):
+                    output_shapes[i][axis[i][d]] = stop - start
+                if start > 0:
+                    output_offset[d] = start
+            else:
+                raise Exception('Crop must be a slice.')
+        if any(o > 0 for o in output_offset):
+            output_offset = numpy.array(output_offset).astype('int64')
+        else:
+            output_offset = None
+    else:
+        output_shapes = [tuple(x.shape) for x in Xs]
+        output_offset = None
+    return output_shapes, output_offset
+
+
+def _normalize_displacement(displacement, Xs, axis):
+    assert _is_array(displacement), 'Displacement matrix should be a numpy.ndarray.'
+    assert displacement.ndim == len(axis[0]) + 1, 'Number of dimensions of displacement does not match input.'
+    assert displacement.shape[0] == len(axis[0]), 'First dimension of displacement should match number of input dimensions.'
+    return displacement
+
+
+def _normalize_order(order, Xs):
+    if not isinstance(order, (tuple, list)):
+        order = [order] * len(Xs)
+    assert len(Xs) == len(order), 'Number of order parameters should be equal to number of inputs.'
+    assert all(0 <= o and o <= 5 for o in order), 'order should be 0, 1, 2, 3, 4 or 5.'
+    return numpy.array(order).astype('int64')
+
+
+def _normalize_mode(mode, Xs):
+    if not isinstance(mode, (tuple, list)):
+        mode = [mode] * len(Xs)
+    mode = [_extend_mode_to_code(o) for o in mode]
+    assert len(Xs) == len(mode), 'Number of mode parameters should be equal to number of inputs.'
+    return numpy.array(mode).astype('int64')
+
+
+def _normalize_cval(cval, Xs):
+    if not isinstance(cval, (tuple, list)):
+        cval = [cval] * len(Xs)
+    assert len(Xs) == len(cval), 'Number of cval parameters should be equal to number of inputs.'
+    return numpy.array(cval).astype('float64')
+
+
+def _normalize_affine(affine, axis):
+    if affine is None:
+        return affine
+    if _is_tensor(affine):
+        affine = affine.detach().cpu().numpy()
+    n_axes = len(axis[0])
+    if affine.shape == (n_axes + 1, n_axes + 1):
+        assert numpy.allclose(affine[n_axes, :], [0, 0, 1]), 'Invalid affine matrix.'
+        affine = affine[:n_axes, :]
+    assert affine.shape == (n_axes, n_axes + 1), 'Affine matrix should have shape (ndim, ndim+1).'
+    return numpy.array(affine).astype('float64')
+
+
+def _compute_inverse_affine(affine):
+    if affine is None:
+        return None
+    else:
+        inverse_affine = numpy.zeros(affine.shape, dtype='float64')
+        inverse_affine[:, :-1] = numpy.linalg.inv(affine[:, :-1])
+        inverse_affine[:, -1] = -numpy.dot(inverse_affine[:, :-1], affine[:, -1])
+        return inverse_affine
+
+
+def _compute_rotation_zoom_affine(angle=None, zoom=None, center=None):
+    """2-D homogeneous matrix: translate(-center) -> rotate -> zoom -> translate(+center) (ref:401-424)."""
+    steps = []
+    if center is not None:
+        steps.append(numpy.array([[1, 0, -center[0]],
+                                  [0, 1, -center[1]],
+                                  [0, 0, 1]]))
+    if angle:
+        theta = numpy.radians(angle)
+        steps.append(numpy.array([[numpy.cos(theta), -numpy.sin(theta), 0],
+                                  [numpy.sin(theta), numpy.cos(theta), 0],
+                                  [0, 0, 1]]))
+    if zoom:
+        steps.append(numpy.array([[zoom, 0, 0],
+                                  [0, zoom, 0],
+                                  [0, 0, 1]]))
+    if center is not None:
+        steps.append(numpy.array([[1, 0, center[0]],
+                                  [0, 1, center[1]],
+                                  [0, 0, 1]]))
+    affine = None
+    for a in steps:
+        affine = a if affine is None else numpy.dot(a, affine)
+    return affine
+
+
+def _apply_rotation_and_zoom(rotate, zoom, inverse_affine, output_shape):
+    if rotate is None and zoom is None:
+        return inverse_affine
+    assert len(output_shape) == 2, 'Zoom and rotate is only implemented for 2D images.'
+    rotate = -float(rotate or 0)
+    zoom = 1 / float(zoom or 1)
+    new_inverse_affine = _compute_rotation_zoom_affine(angle=rotate, zoom=zoom,
+                                                       center=numpy.array(output_shape) / 2 - 0.5)
+    if inverse_affine is not None:
+        base_inverse_affine = numpy.eye(3, dtype='float64')
+        base_inverse_affine[:-1, :] = inverse_affine
+        return numpy.dot(new_inverse_affine, base_inverse_affine)[:2, :]
+    else:
+        return new_inverse_affine[:2, :]
+
+
+_MODE_CODES = {'nearest': 0, 'wrap': 1, 'reflect': 2, 'mirror': 3, 'constant': 4}
+
+
+def _extend_mode_to_code(mode):
+    """Convert an extension mode to the corresponding integer code (ref:440-454)."""
+    try:
+        return _MODE_CODES[mode]
+    except (KeyError, TypeError):
+        raise RuntimeError('boundary mode not supported')
