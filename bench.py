@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the elastic-deformation hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json `metric`): forward + gradient of a 256^3 float32 volume at
+spline order 3 with a 5x5x5 displacement grid (sigma 8), mode 'constant',
+prefilter=False (kernel-only headline).  One "step" = one forward gather +
+the zero-fill of dX + one gradient scatter of one volume per GPU; volumes are
+independent, so N GPUs process N volumes per step (weak scaling, no data-path
+collective; NCCL only for the barrier / max-over-ranks).
+
+Printed keys (one JSON line from rank 0):
+  value         Mvoxels/s fwd+grad, data resident in HBM, C-ABI calls, CUDA-event timed
+  e2e           same metric through the public Python API with pinned HOST arrays
+                (H2D of X and dY, D2H of Y and dX inside the timed region)
+  roofline      the dominant kernel's algorithmic bytes / its CUDA-event duration vs the
+                measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's own C loop (oracle/_ref; else the oracle port) timed on
+                this box's host cores on a bounded sample of the same workload
+`--impl reference` times only that CPU path and prints the same line with
+"impl": "reference".
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPE = (256, 256, 256)
+POINTS = (5, 5, 5)
+SIGMA = 8.0
+ORDER = 3
+NVOX = SHAPE[0] * SHAPE[1] * SHAPE[2]
+ALG_BYTES_FWD = 8 * NVOX          # read X once + write Y once (float32)        SURVEY 8d
+ALG_BYTES_GRAD = 8 * NVOX         # read dY once + write dX once (zero-fill not credited)
+METRIC = "Mvoxels/s fwd+grad (256^3 f32 order=3)"
+
+
+def make_inputs(seed):
+    rng = np.random.default_rng(seed)
+    X = rng.random(SHAPE, dtype=np.float32)
+    dY = rng.random(SHAPE, dtype=np.float32)
+    D = rng.standard_normal((3,) + POINTS) * SIGMA
+    return X, dY, D
+
+
+# ----------------------------------------------------------------------------------------
+# CPU reference arm (also the cpu_baseline leg of the GPU arm)
+# ----------------------------------------------------------------------------------------
+def cpu_reference_rate(X, dY, D, seconds_budget, planes=4, steps=1, max_threads=None):
+    """fwd+grad Mvoxels/s of the reference C loop on the host cores.
+
+    Bounded sample of the 256^3 workload: every host thread deforms its own slab of `planes`
+    z-planes of the SAME volume (crop=(slice(z, z+planes), :, :); the reference's crop computes
+    exactly those output voxels with the displacement field of the full volume), forward and
+    gradient.  The C loop releases the GIL (deform.c:377-379), so threads run in parallel.
+    """
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    kind = "reference" if O.ref_available() else "port"
+    impl = "ref" if kind == "reference" else "port"
+    cores = max_threads or os.cpu_count() or 1
+    nslab = SHAPE[0] // planes
+    cores = min(cores, nslab)
+
+    def job(k):
+        z0 = (k * (nslab // cores)) * planes
+        crop = (slice(z0, z0 + planes), slice(0, SHAPE[1]), slice(0, SHAPE[2]))
+        y = O.deform_grid(X, D, order=ORDER, prefilter=False, crop=crop, impl=impl)
+        g = np.ascontiguousarray(dY[z0:z0 + planes])
+        O.deform_grid_gradient(g, D, order=ORDER, prefilter=False, crop=crop, X_shape=SHAPE, impl=impl)
+        return y.size
+
+    times = []
+    with ThreadPoolExecutor(cores) as ex:
+        list(ex.map(job, range(min(2, cores))))            # warm (page-in, lazy builds)
+        t_all0 = time.perf_counter()
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            vox = sum(ex.map(job, range(cores)))
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_all0 > seconds_budget:
+                break
+    t = float(np.mean(times))
+    sample = ("%d host threads x (%d z-planes of the 256^3 f32 order-3 volume, fwd+grad, "
+              "crop of the full problem) = %d voxels per step" % (cores, planes, vox))
+    return vox / t / 1e6, cores, kind, sample, t, len(times)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    X, dY, D = make_inputs(0)
+    # warmup + steps, bounded to a few minutes in total
+    v, cores, kind, sample, t, nsteps = cpu_reference_rate(X, dY, D, seconds_budget=150.0, planes=4,
+                                                           steps=max(1, min(args.steps, 3)))
+    line = {
+        "metric": METRIC, "value": round(v, 4), "unit": "Mvoxels/s", "impl": "reference",
+        "n_gpus": args.gpus, "steps": nsteps, "warmup": 1, "ms_per_step": round(t * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "256^3 float32, 5x5x5 grid sigma 8, order 3, mode constant, "
+                               "prefilter=False, fwd+grad; bounded sample: " + sample},
+        "cpu_baseline": {"value": round(v, 4), "unit": "Mvoxels/s", "cores": cores, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": round(v, 4), "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------
+# clocks sampler (NVML; falls back to nvidia-smi)
+# ----------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+               0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.active = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                if self.active:
+                    self.samples.append(mhz)
+                    for bit, name in self.REASONS.items():
+                        if r & bit and name != "gpu_idle":
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import importlib
+    import elasticdeform_b200 as edf
+    from elasticdeform_b200 import _lib
+    dg = importlib.import_module("elasticdeform_b200.deform_grid")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load_library()
+
+    # ---- resident data: NSETS buffer sets rotate so that no step re-reads L2-resident inputs
+    NSETS = 4
+    X_h, dY_h, D = make_inputs(rank)
+    sets = []
+    for s in range(NSETS):
+        X = torch.from_numpy(np.roll(X_h, s, axis=0)).to(dev)
+        dY = torch.from_numpy(np.roll(dY_h, s, axis=1)).to(dev)
+        Y = torch.empty_like(X)
+        dX = torch.empty_like(X)
+        sets.append((X, dY, Y, dX))
+    d_f = dg._prefilter_displacement(lib, D, dev)
+    axis = [(0, 1, 2)]
+    order, mode, cval = np.array([ORDER]), np.array([4]), np.array([0.0])
+    probs = []
+    for (X, dY, Y, dX) in sets:
+        pf, kf = dg._build_problem([X], [Y], d_f, None, axis, order, mode, cval, None)
+        pg, kg = dg._build_problem([dX], [dY], d_f, None, axis, order, mode, cval, None)
+        probs.append((pf, pg, kf, kg))
+    stream = torch.cuda.current_stream(dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+
+    def step(i, evs=None):
+        X, dY, Y, dX = sets[i % NSETS]
+        pf, pg, _, _ = probs[i % NSETS]
+        if evs is not None:
+            evs[0].record(stream)
+        _lib.check(lib.edf_deform_grid(ctypes.byref(pf), sp))
+        if evs is not None:
+            evs[1].record(stream)
+        dX.zero_()
+        if evs is not None:
+            evs[2].record(stream)
+        _lib.check(lib.edf_deform_grid_grad(ctypes.byref(pg), sp))
+        if evs is not None:
+            evs[3].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    fwd_kernel = _lib.last_kernel()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count()
+    sampler.active = True
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i, evs[i])
+    e1.record(stream)
+    barrier()
+    sampler.active = False
+    launches = _lib.launch_count() - launches0 + args.steps      # + the zero-fill kernels (torch)
+    ms_total = e0.elapsed_time(e1)
+    t_fwd = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    t_zero = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    t_grad = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = float(tmax.item())
+    ms_step = ms_total / args.steps
+    value = NVOX * world / (ms_step * 1e-3) / 1e6
+
+    # ---- parity spot check on the very arrays that were timed (a slab, vs the oracle)
+    parity = None
+    if rank == 0:
+        try:
+            from oracle import oracle as O
+            impl = "ref" if O.ref_available() else "port"
+            crop = (slice(128, 130), slice(0, 256), slice(0, 256))
+            X, dY, Y, dX = sets[0]
+            step(0)
+            torch.cuda.synchronize(dev)
+            yref = O.deform_grid(X.cpu().numpy(), D, order=ORDER, prefilter=False, crop=crop, impl=impl)
+            parity = {"fwd_max_abs_err_slab": float(np.abs(Y[128:130].cpu().numpy() - yref).max()), "tol": 1e-5}
+        except Exception as e:                                   # pragma: no cover
+            parity = {"error": repr(e)}
+
+    # ---- e2e: public API, pinned host arrays in and out, every step
+    Xp = torch.empty(SHAPE, dtype=torch.float32).pin_memory()
+    Gp = torch.empty(SHAPE, dtype=torch.float32).pin_memory()
+    Xp.copy_(torch.from_numpy(X_h))
+    Gp.copy_(torch.from_numpy(dY_h))
+    Xn, Gn = Xp.numpy(), Gp.numpy()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        y = edf.deform_grid(Xn, D, order=ORDER, prefilter=False)
+        dx = edf.deform_grid_gradient(Gn, D, order=ORDER, prefilter=False)
+        return y, dx
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        y, dx = e2e_step()
+    torch.cuda.synchronize(dev)
+    t_e2e = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e = float(te.item())
+    e2e_value = NVOX * world / t_e2e / 1e6
+
+    # default-API variant (prefilter=True) for information
+    for _ in range(1):
+        edf.deform_grid(Xn, D, order=ORDER)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    edf.deform_grid(Xn, D, order=ORDER)
+    edf.deform_grid_gradient(Gn, D, order=ORDER)
+    torch.cuda.synchronize(dev)
+    t_e2e_pf = time.perf_counter() - t0
+
+    sampler.stop()
+    clocks = sampler.summary()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        if t_grad >= t_fwd:
+            dom, t_dom, alg = "gradient scatter (" + _lib.last_kernel() + ")", t_grad, ALG_BYTES_GRAD
+        else:
+            dom, t_dom, alg = "forward gather (" + fwd_kernel + ")", t_fwd, ALG_BYTES_FWD
+        achieved = alg / (t_dom * 1e-3) / 1e9
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get("grad" if t_grad >= t_fwd else "fwd")
+        except Exception:
+            pass
+        ach_f = ALG_BYTES_FWD / (t_fwd * 1e-3) / 1e9
+        ach_g = ALG_BYTES_GRAD / (t_grad * 1e-3) / 1e9
+        cpu = None
+        if world == 1 or True:
+            try:
+                v, cores, kind, sample, t, _ = cpu_reference_rate(X_h, dY_h, D, seconds_budget=30.0, planes=2, steps=1)
+                cpu = {"value": round(v, 4), "unit": "Mvoxels/s", "cores": cores, "kind": kind, "sample": sample}
+            except Exception as e:                               # pragma: no cover
+                cpu = {"error": repr(e)}
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": "Mvoxels/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "256^3 float32 volume per GPU, 5x5x5 grid sigma 8, order 3, mode constant, "
+                                   "prefilter=False; step = forward gather + dX zero-fill + gradient scatter",
+                       "l2": "inputs larger than L2: %d rotating buffer sets (%.2f GB) vs 126 MB L2"
+                             % (NSETS, NSETS * 4 * 4 * NVOX / 1e9),
+                       "sharding": "one independent volume per GPU per step, no data-path collective"},
+            "e2e": {"value": round(e2e_value, 1), "unit": "Mvoxels/s",
+                    "h2d_bytes_per_step": 2 * 4 * NVOX, "d2h_bytes_per_step": 2 * 4 * NVOX,
+                    "ms_per_step": round(t_e2e * 1e3, 3),
+                    "api": "elasticdeform_b200.deform_grid + deform_grid_gradient on pinned NumPy arrays",
+                    "default_prefilter_ms_per_step": round(t_e2e_pf * 1e3, 3)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 1), "peak": peak,
+                         "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg, "kernel_ms": round(t_dom, 4)},
+            "kernels": {"fwd_ms": round(t_fwd, 4), "zero_fill_ms": round(t_zero, 4), "grad_ms": round(t_grad, 4),
+                        "fwd_GBps": round(ach_f, 1), "fwd_frac": round(ach_f / peak, 4),
+                        "grad_GBps": round(ach_g, 1), "grad_frac": round(ach_g / peak, 4),
+                        "fwd_kernel": fwd_kernel},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "parity": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

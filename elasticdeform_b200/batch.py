@@ -1,0 +1,90 @@
+"""Batched entry: many independent volumes, each with its own displacement / affine.
+
+The reference has no batch dimension -- a batch is a Python loop around
+``deform_grid`` (reference README.md:117-133), one single-threaded C call per
+volume.  Here the whole batch is handed to the C-ABI in ONE call
+(``edf_deform_grid_batch``), which enqueues the kernels back to back on one stream,
+and batches shard across GPUs by volume (one process per GPU, no exchange).
+"""
+import ctypes
+import importlib
+
+import numpy
+
+from . import _lib
+
+_dg = importlib.import_module(__package__ + ".deform_grid")
+
+
+def shard_range(n_items, rank, world_size):
+    """Contiguous block of `n_items` independent volumes owned by `rank` (sizes differ by <= 1)."""
+    base, rem = divmod(int(n_items), int(world_size))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def deform_grid_batch(Xs, displacements, order=3, mode='constant', cval=0.0, crop=None,
+                      prefilter=True, affines=None, gradient=False, X_shape=None, _flags=0):
+    """Deform every volume Xs[b] with its own displacements[b] (and affines[b]).
+
+    Same per-volume semantics as ``deform_grid`` (or ``deform_grid_gradient`` with
+    ``gradient=True``, where Xs are the upstream gradients and ``X_shape`` the common
+    input shape).  Volumes may be NumPy arrays or CUDA tensors; returns a list.
+    """
+    torch = _dg.torch
+    lib = _dg._require_cuda()
+    nb = len(Xs)
+    assert len(displacements) == nb, 'one displacement per volume'
+    if affines is not None:
+        assert len(affines) == nb, 'one affine per volume'
+    device = _dg._device_of(Xs)
+    problems = (_lib.EdfProblem * nb)()
+    keep, outs, dxs = [], [], []
+    with torch.cuda.device(device):
+        for b in range(nb):
+            X = [Xs[b]]
+            if gradient:
+                shp = tuple(X_shape) if X_shape is not None else tuple(Xs[b].shape)
+                meta = [_dg._ShapeOnly(shp)]
+            else:
+                meta = X
+            axis, deform_shape = _dg._normalize_axis_list(None, meta)
+            out_shapes, offset = _dg._compute_output_shapes(meta, axis, deform_shape, crop)
+            od = _dg._normalize_order(order, X)
+            md = _dg._normalize_mode(mode, X)
+            cv = _dg._normalize_cval(cval, X)
+            inv = _dg._compute_inverse_affine(_dg._normalize_affine(None if affines is None else affines[b], axis))
+            d_f = _dg._prefilter_displacement(lib, _dg._normalize_displacement(displacements[b], X, axis), device)
+            xd = _dg._to_device(Xs[b], device)
+            if gradient:
+                if tuple(out_shapes[0]) != tuple(xd.shape):
+                    raise ValueError("X_shape does not match output shape and cropping.")
+                dx = torch.zeros(shp, dtype=xd.dtype, device=device)
+                pr, k = _dg._build_problem([dx], [xd], d_f, offset, axis, od, md, cv, inv, _flags)
+                dxs.append(dx)
+            else:
+                src = xd
+                if prefilter and od[0] > 1:
+                    x_f = torch.empty_like(xd)
+                    for ax in axis[0]:
+                        _dg._spline_filter1d_device(lib, src, x_f, ax, int(od[0]))
+                        src = x_f
+                out = torch.empty(tuple(out_shapes[0]), dtype=xd.dtype, device=device)
+                pr, k = _dg._build_problem([src], [out], d_f, offset, axis, od, md, cv, inv, _flags)
+                outs.append(out)
+            problems[b] = pr
+            keep.append(k)
+        _lib.check(lib.edf_deform_grid_batch(problems, nb, 1 if gradient else 0, _dg._stream_ptr(device)))
+        if gradient:
+            res = []
+            for b, dx in enumerate(dxs):
+                if prefilter and int(_dg._normalize_order(order, [0])[0]) > 1:
+                    x_f = torch.empty_like(dx)
+                    src = dx
+                    for ax in range(dx.ndim):
+                        _dg._spline_filter1d_device(lib, src, x_f, ax, int(_dg._normalize_order(order, [0])[0]), adjoint=True)
+                        src = x_f
+                    dx = x_f
+                res.append(_dg._from_device(dx, Xs[b]))
+            return res
+        return [_dg._from_device(o, x) for o, x in zip(outs, Xs)]

@@ -116,8 +116,11 @@ def _prefilter_displacement(lib, displacement, device):
     return d_f
 
 
-def _launch(lib, gradient, ins, outs, displacement_f, output_offset, axis, order, mode, cval,
-            inverse_affine, flags=0):
+def _build_problem(ins, outs, displacement_f, output_offset, axis, order, mode, cval,
+                   inverse_affine, flags=0):
+    """Fill an edf_problem (include/edf_b200.h) -- the arguments of the reference's
+    _deform_grid.deform_grid(...) call (ref:174 / ref:274) as plain pointers.
+    Returns (problem, keepalive)."""
     n = len(ins)
     naxis = len(axis[0])
     if n > _lib.EDF_MAX_INPUTS:
@@ -132,7 +135,7 @@ def _launch(lib, gradient, ins, outs, displacement_f, output_offset, axis, order
     pr.inputs = in_arr
     pr.outputs = out_arr
     pr.displacement = _edf_array(displacement_f)
-    keep = [in_arr, out_arr]
+    keep = [in_arr, out_arr, ins, outs, displacement_f]
     if output_offset is not None:
         off = (ctypes.c_int64 * naxis)(*[int(v) for v in output_offset])
         pr.output_offset = off
@@ -149,6 +152,13 @@ def _launch(lib, gradient, ins, outs, displacement_f, output_offset, axis, order
         pr.affine = af
         keep.append(af)
     pr.flags = int(flags)
+    return pr, keep
+
+
+def _launch(lib, gradient, ins, outs, displacement_f, output_offset, axis, order, mode, cval,
+            inverse_affine, flags=0):
+    pr, keep = _build_problem(ins, outs, displacement_f, output_offset, axis, order, mode, cval,
+                              inverse_affine, flags)
     fn = lib.edf_deform_grid_grad if gradient else lib.edf_deform_grid
     _lib.check(fn(ctypes.byref(pr), _stream_ptr(ins[0].device)))
 
@@ -157,7 +167,16 @@ def _from_device(t, like):
     """Return the result in the same kind of container as the corresponding input."""
     if _is_tensor(like):
         return t if like.is_cuda else t.to(like.device)
-    return t.cpu().numpy()
+    # NumPy caller: device -> pinned host block from torch's caching host allocator (the block
+    # returns to the cache when the caller drops the array), so repeated calls copy at full
+    # PCIe speed without a fresh cudaHostAlloc each time.
+    try:
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    except RuntimeError:
+        return t.cpu().numpy()
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
 
 
 # --------------------------------------------------------------------------------------

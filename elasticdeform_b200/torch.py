@@ -10,7 +10,8 @@ from __future__ import absolute_import
 
 import torch
 
-from . import deform_grid as _dg
+from .deform_grid import deform_grid as _deform_grid
+from .deform_grid import deform_grid_gradient as _deform_grid_gradient
 
 
 class ElasticDeform(torch.autograd.Function):
@@ -21,14 +22,14 @@ class ElasticDeform(torch.autograd.Function):
         ctx.deform_kwargs = deform_kwargs
         ctx.x_shapes = [tuple(x.shape) for x in xs]
 
-        ys = _dg.deform_grid([x.detach() for x in xs], displacement.detach(),
+        ys = _deform_grid([x.detach() for x in xs], displacement.detach(),
                              *deform_args, **deform_kwargs)
         return tuple(ys)
 
     @staticmethod
     def backward(ctx, *dys):
         displacement, = ctx.saved_tensors
-        dxs = _dg.deform_grid_gradient([dy.detach() for dy in dys], displacement.detach(),
+        dxs = _deform_grid_gradient([dy.detach() for dy in dys], displacement.detach(),
                                        *ctx.deform_args, X_shape=ctx.x_shapes, **ctx.deform_kwargs)
         return (None, None, None) + tuple(dxs)
 

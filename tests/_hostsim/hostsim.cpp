@@ -72,3 +72,38 @@ extern "C" int hostsim_fast_coords(const edf_problem* pr, int input_index, int64
     if (rc != EDF_OK) return rc;
     return edf_fast_coords_host(p, input_index, starts, fracs, constant, n_exact);
 }
+
+// Reference-order coordinates (exact displacement evaluation for every voxel), same outputs
+// as hostsim_fast_coords: what the fast pipeline has to reproduce.
+template <int NAXIS>
+static void exact_coords_n(const EdfParams& p, int ii, int64_t* starts, float* fracs, uint8_t* constant)
+{
+    const EdfInputDesc& d = p.inp[ii];
+    for (int64_t kk = 0; kk < p.size; ++kk) {
+        int64_t o[NAXIS], r = kk;
+        for (int a = NAXIS - 1; a >= 0; --a) { o[a] = r % p.odim[a]; r /= p.odim[a]; }
+        double dd[NAXIS];
+        edf_displacement_exact<NAXIS>(p, o, dd);
+        bool cst = false;
+        for (int h = 0; h < NAXIS; ++h) {
+            int st = 0; float fr = 0.f;
+            const double in = edf_source_coordinate<NAXIS>(p, o, h, dd[h]);
+            if (!cst && !edf_fast_finish(p, d.mode, d.order, h, in, &st, &fr)) cst = true;
+            starts[kk * NAXIS + h] = cst ? 0 : st;
+            fracs[kk * NAXIS + h] = cst ? 0.f : fr;
+        }
+        constant[kk] = cst ? 1 : 0;
+    }
+}
+
+extern "C" int hostsim_exact_coords(const edf_problem* pr, int input_index, int64_t* starts,
+                                    float* fracs, uint8_t* constant)
+{
+    EdfParams p;
+    int rc = flatten_problem(pr, 0, p);
+    if (rc != EDF_OK) return rc;
+    if (p.naxis == 3) exact_coords_n<3>(p, input_index, starts, fracs, constant);
+    else if (p.naxis == 2) exact_coords_n<2>(p, input_index, starts, fracs, constant);
+    else return edf_fail(EDF_ERR_RUNTIME, "naxis must be 2 or 3");
+    return 0;
+}

@@ -102,8 +102,10 @@ class HostSimModule(object):
         _check(lib().hostsim_filter(ctypes.byref(a), ctypes.byref(b), int(axis), int(order), 0))
 
 
-def fast_coords(inputs, displacement, output_offset, outputs, axis, orders, modes, cvals, affine, ii=0):
-    """Window starts / fractional offsets / constant flags the fast kernels derive."""
+def fast_coords(inputs, displacement, output_offset, outputs, axis, orders, modes, cvals, affine, ii=0,
+                exact=False):
+    """Window starts / fractional offsets / constant flags the fast kernels derive
+    (exact=True: the same quantities from the reference-order evaluation of every voxel)."""
     pr, keep = _problem(inputs, displacement, output_offset, outputs, axis, orders, modes, cvals, affine)
     naxis = len(axis[0])
     nvox = int(np.prod([outputs[0].shape[a] for a in axis[0]]))
@@ -111,6 +113,11 @@ def fast_coords(inputs, displacement, output_offset, outputs, axis, orders, mode
     fracs = np.zeros((nvox, naxis), dtype=np.float32)
     const = np.zeros(nvox, dtype=np.uint8)
     nex = ctypes.c_int64(0)
+    if exact:
+        _check(lib().hostsim_exact_coords(ctypes.byref(pr), int(ii), starts.ctypes.data_as(ctypes.c_void_p),
+                                          fracs.ctypes.data_as(ctypes.c_void_p),
+                                          const.ctypes.data_as(ctypes.c_void_p)))
+        return starts, fracs, const, 0
     _check(lib().hostsim_fast_coords(ctypes.byref(pr), int(ii), starts.ctypes.data_as(ctypes.c_void_p),
                                      fracs.ctypes.data_as(ctypes.c_void_p),
                                      const.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nex)))

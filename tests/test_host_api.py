@@ -1,0 +1,159 @@
+"""Host logic and C-ABI surface (CPU only; no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import elasticdeform_b200 as edf
+import importlib
+
+from elasticdeform_b200 import _lib
+
+dg = importlib.import_module("elasticdeform_b200.deform_grid")   # the module, not the function
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol(built_library):
+    header = open(os.path.join(ROOT, "include", "edf_b200.h")).read()
+    declared = set(re.findall(r"\b(edf_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    lib = _lib.load_library()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.edf_version() >= 100
+
+
+def test_struct_layout_matches_header():
+    assert ctypes.sizeof(_lib.EdfArray) == 8 + 4 + 4 + 8 * 8 + 8 * 8
+    assert _lib.EdfProblem.displacement.offset == 24
+    assert ctypes.sizeof(_lib.EdfProblem) == 24 + ctypes.sizeof(_lib.EdfArray) + 6 * 8 + 8
+
+
+def test_public_names_and_signatures_match_reference():
+    import inspect
+    assert edf.__all__ == ["deform_random_grid", "deform_grid", "deform_grid_gradient"]
+    p = list(inspect.signature(edf.deform_grid).parameters)
+    assert p[:11] == ["X", "displacement", "order", "mode", "cval", "crop", "prefilter", "axis",
+                      "affine", "rotate", "zoom"]
+    p = list(inspect.signature(edf.deform_grid_gradient).parameters)
+    assert p[:12] == ["dY", "displacement", "order", "mode", "cval", "crop", "prefilter", "axis",
+                      "X_shape", "affine", "rotate", "zoom"]
+    p = list(inspect.signature(edf.deform_random_grid).parameters)
+    assert p[:12] == ["X", "sigma", "points", "order", "mode", "cval", "crop", "prefilter", "axis",
+                      "affine", "rotate", "zoom"]
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        edf.deform_grid(np.zeros((8, 8)), np.zeros((2, 3, 3)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        edf.deform_grid_gradient(np.zeros((8, 8)), np.zeros((2, 3, 3)))
+    # the C-ABI itself refuses too (status EDF_ERR_CUDA), it does not compute on the host
+    lib = _lib.load_library()
+    pr = _lib.EdfProblem()
+    assert lib.edf_deform_grid(ctypes.byref(pr), None) == -4
+    assert b"no CPU fallback" in lib.edf_last_error()
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "elasticdeform_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("oracle/", "").lower() or f == "edf_core.h" or \
+                    "import oracle" not in src and "from oracle" not in src, f
+                assert "import oracle" not in src and "from oracle" not in src, f
+                assert "/root/reference" not in src, f
+
+
+# ---- argument normalisation: same behaviour as reference deform_grid.py:295-454 -----------
+def test_normalize_inputs_errors():
+    with pytest.raises(Exception, match="X should be a numpy.ndarray"):
+        dg._normalize_inputs((np.zeros(3),))
+    with pytest.raises(AssertionError):
+        dg._normalize_inputs([])
+    with pytest.raises(AssertionError):
+        dg._normalize_inputs([1, 2])
+
+
+def test_axis_normalisation():
+    X, Y = np.zeros((3, 20, 30)), np.zeros((20, 30))
+    ax, shp = dg._normalize_axis_list([(1, 2), (0, 1)], [X, Y])
+    assert ax == [(1, 2), (0, 1)] and shp == (20, 30)
+    ax, shp = dg._normalize_axis_list(None, [Y])
+    assert ax == [(0, 1)]
+    ax, shp = dg._normalize_axis_list(1, [X])
+    assert ax == [(1,)] and shp == (20,)
+    with pytest.raises(AssertionError, match="same length"):
+        dg._normalize_axis_list(None, [X, Y])
+    with pytest.raises(AssertionError, match="same shape"):
+        dg._normalize_axis_list(None, [Y, np.zeros((20, 31))])
+    with pytest.raises(AssertionError, match="sorted and unique"):
+        dg._normalize_axis_list((2, 1), [X])
+    with pytest.raises(AssertionError, match="invalid axis"):
+        dg._normalize_axis_list((1, 3), [X])
+
+
+def test_crop_normalisation():
+    X = np.zeros((3, 20, 30))
+    shapes, off = dg._compute_output_shapes([X], [(1, 2)], (20, 30), (slice(5, 15), slice(0, 30)))
+    assert shapes == [[3, 10, 30]] and off.tolist() == [5, 0] and off.dtype == np.int64
+    shapes, off = dg._compute_output_shapes([X], [(1, 2)], (20, 30), (slice(0, 15), slice(None)))
+    assert off is None and shapes == [[3, 15, 30]]
+    with pytest.raises(Exception, match="Crop must be a slice"):
+        dg._compute_output_shapes([X], [(1, 2)], (20, 30), (3, slice(None)))
+    with pytest.raises(AssertionError):
+        dg._compute_output_shapes([X], [(1, 2)], (20, 30), (slice(0, 25), slice(None)))
+
+
+def test_mode_order_cval():
+    X = [np.zeros(3), np.zeros(3)]
+    assert dg._normalize_mode(["constant", "reflect"], X).tolist() == [4, 2]
+    assert dg._normalize_mode("nearest", X).tolist() == [0, 0]
+    with pytest.raises(RuntimeError, match="boundary mode not supported"):
+        dg._normalize_mode("bogus", X)
+    with pytest.raises(AssertionError, match="order should be"):
+        dg._normalize_order(6, X)
+    assert dg._normalize_order([0, 3], X).dtype == np.int64
+    assert dg._normalize_cval(1, X).tolist() == [1.0, 1.0]
+
+
+def test_affine_and_rotate_zoom_match_oracle_glue():
+    from oracle import oracle as O
+    rng = np.random.default_rng(0)
+    A = np.array([[1.1, 0.2, 3.0], [-0.1, 0.9, -2.0]])
+    inv = dg._compute_inverse_affine(dg._normalize_affine(A, [(0, 1)]))
+    np.testing.assert_array_equal(inv, O._inverse_affine(A, 2))
+    A3 = np.vstack([A, [0, 0, 1]])
+    np.testing.assert_array_equal(dg._normalize_affine(A3, [(0, 1)]), A)
+    for rot, zoom in [(30, None), (None, 1.5), (-20, 0.5), (0, 1.0)]:
+        a = dg._apply_rotation_and_zoom(rot, zoom, inv, [40, 50])
+        b = O._rot_zoom(rot, zoom, inv, [40, 50])
+        np.testing.assert_array_equal(a, b)
+        a = dg._apply_rotation_and_zoom(rot, zoom, None, [40, 50])
+        b = O._rot_zoom(rot, zoom, None, [40, 50])
+        np.testing.assert_array_equal(a, b)
+    with pytest.raises(AssertionError, match="only implemented for 2D"):
+        dg._apply_rotation_and_zoom(10, None, None, [4, 5, 6])
+
+
+def test_gradient_shape_errors_raise_before_any_device_work():
+    with pytest.raises(ValueError, match="X_shape is required"):
+        edf.deform_grid_gradient(np.zeros((5, 5)), np.zeros((2, 3, 3)), crop=(slice(0, 5), slice(0, 5)))
+    with pytest.raises(ValueError, match="X_shape does not match"):
+        edf.deform_grid_gradient(np.zeros((5, 5)), np.zeros((2, 3, 3)), X_shape=(6, 6))
+
+
+def test_dtype_codes():
+    assert _lib.dtype_code(np.float32) == 9 and _lib.dtype_code("int32") == 7
+    with pytest.raises(RuntimeError, match="data type not supported"):
+        _lib.dtype_code(np.float16)
+    with pytest.raises(RuntimeError, match="data type not supported"):
+        _lib.dtype_code(np.complex64)
