@@ -15,7 +15,8 @@
 #include "edf_fast_core.h"
 
 #define EDF_FAST_G 4               // thread groups (slabs in 3-D, row blocks in 2-D)
-#define EDF_FAST_M 8               // rows per group
+#define EDF_FAST_M 8               // rows per group and chunk
+#define EDF_FAST_RY 64             // rows (second-last axis) a CTA walks through, chunk by chunk
 #define EDF_FAST_THREADS (EDF_FAST_TX * EDF_FAST_G)
 
 struct EdfFastLaunch {
@@ -26,91 +27,114 @@ struct EdfFastLaunch {
     int32_t  ostr_e[EDF_MAX_INPUTS][EDF_MAX_AXIS];
 };
 
+// rows of the second-last axis processed per chunk: 3-D: M rows for each of the G slabs,
+// 2-D: G*M consecutive rows
 template <int NAXIS>
-struct EdfFastSmem {
-    static constexpr int NROWS = (NAXIS == 3) ? EDF_FAST_M : EDF_FAST_G * EDF_FAST_M;
+struct EdfFastGeom {
+    static constexpr int CHUNK_ROWS = (NAXIS == 3) ? EDF_FAST_M : EDF_FAST_G * EDF_FAST_M;
+    static constexpr int NCHUNK = EDF_FAST_RY / CHUNK_ROWS;
     static constexpr int NSLAB = (NAXIS == 3) ? EDF_FAST_G : 1;
-    double wz[EDF_FAST_G][4];
-    double wy[NROWS][4];
-    double wx[EDF_FAST_TX][4];
-    int    sz[EDF_FAST_G];
-    int    sy[NROWS];
-    int    sx[EDF_FAST_TX];
-    double A[NAXIS][NSLAB][EDF_FAST_NC][EDF_FAST_NC];
-    double B[NAXIS][EDF_FAST_G][EDF_FAST_M][EDF_FAST_NC];
-    int    nonzero;
 };
 
+template <int NAXIS>
+struct EdfFastSmem {
+    double wz[EDF_FAST_G][4];
+    double wy[EDF_FAST_RY][4];
+    double wx[EDF_FAST_TX][4];
+    int    sz[EDF_FAST_G];
+    int    sy[EDF_FAST_RY];
+    int    sx[EDF_FAST_TX];
+    int    ny, nx, nonzero, pad_;
+    double A[NAXIS][EdfFastGeom<NAXIS>::NSLAB][EDF_FAST_NC][EDF_FAST_NC];
+    double B[2][NAXIS][EDF_FAST_G][EDF_FAST_M][EDF_FAST_NC];     // double buffered per chunk
+};
+
+__device__ __forceinline__ int edf_mirror_index32(int idx, int len)
+{
+    if ((unsigned)idx < (unsigned)len) return idx;           // interior: no division
+    return (int)edf_mirror_index((int64_t)idx, (int64_t)len);
+}
+
 // ---------------------------------------------------------------------------------------
-// tile prologue: per-axis control tables, then the separable contractions A (over z)
-// and B (over y) of the displacement coefficients
+// CTA prologue: per-axis control tables for the whole tile, then the z-contraction A of
+// the displacement coefficients restricted to the control points the tile touches
 // ---------------------------------------------------------------------------------------
 template <int NAXIS>
 __device__ __forceinline__ void edf_fast_tile_setup(const EdfParams& p, EdfFastSmem<NAXIS>& s,
                                                     int64_t z0, int64_t y0, int64_t x0)
 {
     constexpr int AX = NAXIS - 1, AY = NAXIS - 2;
-    constexpr int NROWS = EdfFastSmem<NAXIS>::NROWS;
-    constexpr int NSLAB = EdfFastSmem<NAXIS>::NSLAB;
+    constexpr int NSLAB = EdfFastGeom<NAXIS>::NSLAB;
     const int tid = threadIdx.x;
     if (tid == 0) s.nonzero = 0;
-    // 64 + NROWS + G table entries, one thread each
     if (tid < EDF_FAST_TX) {
         const int64_t o = min(x0 + tid, p.odim[AX] - 1);
         edf_fast_ctrl_entry(p, AX, o, s.wx[tid], &s.sx[tid]);
-    } else if (tid < EDF_FAST_TX + NROWS) {
+    } else if (tid < EDF_FAST_TX + EDF_FAST_RY) {
         const int t = tid - EDF_FAST_TX;
         const int64_t o = min(y0 + t, p.odim[AY] - 1);
         edf_fast_ctrl_entry(p, AY, o, s.wy[t], &s.sy[t]);
-    } else if (NAXIS == 3 && tid < EDF_FAST_TX + NROWS + EDF_FAST_G) {
-        const int t = tid - EDF_FAST_TX - NROWS;
+    } else if (NAXIS == 3 && tid < EDF_FAST_TX + EDF_FAST_RY + EDF_FAST_G) {
+        const int t = tid - EDF_FAST_TX - EDF_FAST_RY;
         const int64_t o = min(z0 + t, p.odim[0] - 1);
         edf_fast_ctrl_entry(p, 0, o, s.wz[t], &s.sz[t]);
     }
     __syncthreads();
     const int sy_min = s.sy[0], sx_min = s.sx[0];
+    const int ny = s.sy[EDF_FAST_RY - 1] - sy_min + 4;        // control rows / columns touched
+    const int nx = s.sx[EDF_FAST_TX - 1] - sx_min + 4;        // (<= EDF_FAST_NC, host-checked)
+    if (tid == 0) { s.ny = ny; s.nx = nx; }
     bool nz = false;
-    constexpr int NA = NAXIS * NSLAB * EDF_FAST_NC * EDF_FAST_NC;
-    for (int e = tid; e < NA; e += EDF_FAST_THREADS) {
-        const int jx = e % EDF_FAST_NC;
-        const int jy = (e / EDF_FAST_NC) % EDF_FAST_NC;
-        const int t = (e / (EDF_FAST_NC * EDF_FAST_NC)) % NSLAB;
-        const int h = e / (EDF_FAST_NC * EDF_FAST_NC * NSLAB);
-        const int64_t my = edf_mirror_index(sy_min + jy, p.ncp[AY]);
-        const int64_t mx = edf_mirror_index(sx_min + jx, p.ncp[AX]);
+    const int na = NAXIS * NSLAB * ny * nx;
+    for (int e = tid; e < na; e += EDF_FAST_THREADS) {
+        const int jx = e % nx;
+        const int jy = (e / nx) % ny;
+        const int t = (e / (nx * ny)) % NSLAB;
+        const int h = e / (nx * ny * NSLAB);
+        const int my = edf_mirror_index32(sy_min + jy, (int)p.ncp[AY]);
+        const int mx = edf_mirror_index32(sx_min + jx, (int)p.ncp[AX]);
         double a = 0.0;
         if (NAXIS == 3) {
             const char* base = p.disp + p.dstr[0] * h + my * p.dstr[2] + mx * p.dstr[3];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int64_t mz = edf_mirror_index(s.sz[t] + i, p.ncp[0]);
-                const double c = edf_load(base + mz * p.dstr[1], p.ddtype);
+                const int mz = edf_mirror_index32(s.sz[t] + i, (int)p.ncp[0]);
+                const double c = (p.ddtype == EDF_F64) ? *(const double*)(base + mz * p.dstr[1])
+                                                       : (double)*(const float*)(base + mz * p.dstr[1]);
                 nz |= (c != 0.0);
                 a = fma(c, s.wz[t][i], a);
             }
         } else {
-            a = edf_load(p.disp + p.dstr[0] * h + my * p.dstr[1] + mx * p.dstr[2], p.ddtype);
+            const char* q = p.disp + p.dstr[0] * h + my * p.dstr[1] + mx * p.dstr[2];
+            a = (p.ddtype == EDF_F64) ? *(const double*)q : (double)*(const float*)q;
             nz |= (a != 0.0);
         }
         s.A[h][t][jy][jx] = a;
     }
     if (nz) s.nonzero = 1;                      // benign race: all writers store 1
     __syncthreads();
-    constexpr int NB = NAXIS * EDF_FAST_G * EDF_FAST_M * EDF_FAST_NC;
-    for (int e = tid; e < NB; e += EDF_FAST_THREADS) {
-        const int jx = e % EDF_FAST_NC;
-        const int m = (e / EDF_FAST_NC) % EDF_FAST_M;
-        const int g = (e / (EDF_FAST_NC * EDF_FAST_M)) % EDF_FAST_G;
-        const int h = e / (EDF_FAST_NC * EDF_FAST_M * EDF_FAST_G);
-        const int row = (NAXIS == 3) ? m : g * EDF_FAST_M + m;
+}
+
+// y-contraction B of chunk c (rows c*CHUNK_ROWS ...) into buffer `buf`
+template <int NAXIS>
+__device__ __forceinline__ void edf_fast_chunk_setup(EdfFastSmem<NAXIS>& s, int c, int buf)
+{
+    const int nx = s.nx;
+    const int sy_min = s.sy[0];
+    const int nb = NAXIS * EDF_FAST_G * EDF_FAST_M * nx;
+    for (int e = threadIdx.x; e < nb; e += EDF_FAST_THREADS) {
+        const int jx = e % nx;
+        const int m = (e / nx) % EDF_FAST_M;
+        const int g = (e / (nx * EDF_FAST_M)) % EDF_FAST_G;
+        const int h = e / (nx * EDF_FAST_M * EDF_FAST_G);
+        const int row = c * EdfFastGeom<NAXIS>::CHUNK_ROWS + ((NAXIS == 3) ? m : g * EDF_FAST_M + m);
         const int t = (NAXIS == 3) ? g : 0;
         const int r0 = s.sy[row] - sy_min;
         double b = 0.0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) b = fma(s.A[h][t][r0 + j][jx], s.wy[row][j], b);
-        s.B[h][g][m][jx] = b;
+        s.B[buf][h][g][m][jx] = b;
     }
-    __syncthreads();
 }
 
 // exact reference-order displacement, kept out of line so that its index tables do not
@@ -125,7 +149,7 @@ __device__ __noinline__ void edf_displacement_exact_cold(const EdfParams& p, con
 // of the voxels that sit next to a discontinuity
 template <int NAXIS>
 __device__ __forceinline__ void edf_fast_voxel_coords(const EdfParams& p, const EdfFastSmem<NAXIS>& s,
-                                                      const int64_t* o, int g, int m, int tx,
+                                                      int buf, const int64_t* o, int g, int m,
                                                       const double* wx, int sxrel, double* in)
 {
     bool danger = false;
@@ -133,7 +157,7 @@ __device__ __forceinline__ void edf_fast_voxel_coords(const EdfParams& p, const 
     for (int h = 0; h < NAXIS; ++h) {
         double d = 0.0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) d = fma(s.B[h][g][m][sxrel + k], wx[k], d);
+        for (int k = 0; k < 4; ++k) d = fma(s.B[buf][h][g][m][sxrel + k], wx[k], d);
         in[h] = edf_source_coordinate<NAXIS>(p, o, h, d);
         danger |= edf_near_half_integer(in[h]);
     }
@@ -158,44 +182,66 @@ __device__ __forceinline__ void edf_fast_tap_offsets(int start, int len, int str
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// float32 kernel: forward gather (GRAD=false) or gradient scatter (GRAD=true)
-// ---------------------------------------------------------------------------------------
-template <int NAXIS, int ORDER, bool GRAD>
-__global__ void __launch_bounds__(EDF_FAST_THREADS)
-edf_fast_f32_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L)
+// Tile walker shared by all fast kernels: calls body(o, in) for every output voxel of the CTA's
+// tile, `in` being the un-mapped source coordinates.
+template <int NAXIS, typename Body>
+__device__ __forceinline__ void edf_fast_walk_tile(const EdfParams& p, EdfFastSmem<NAXIS>& s, Body& body)
 {
-    __shared__ EdfFastSmem<NAXIS> s;
     constexpr int AX = NAXIS - 1, AY = NAXIS - 2;
-    constexpr int NT = ORDER + 1;
+    constexpr int NCHUNK = EdfFastGeom<NAXIS>::NCHUNK;
+    constexpr int CHUNK_ROWS = EdfFastGeom<NAXIS>::CHUNK_ROWS;
     const int64_t x0 = (int64_t)blockIdx.x * EDF_FAST_TX;
-    const int64_t y0 = (int64_t)blockIdx.y * EdfFastSmem<NAXIS>::NROWS;
+    const int64_t y0 = (int64_t)blockIdx.y * EDF_FAST_RY;
     const int64_t z0 = (int64_t)blockIdx.z * EDF_FAST_G;
     edf_fast_tile_setup<NAXIS>(p, s, z0, y0, x0);
 
     const int tx = threadIdx.x & (EDF_FAST_TX - 1);
     const int g = threadIdx.x >> 6;
     const int64_t x = x0 + tx;
-    if (x >= p.odim[AX]) return;
+    const bool xok = x < p.odim[AX];
     double wx[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) wx[k] = s.wx[tx][k];
     const int sxrel = s.sx[tx] - s.sx[0];
+    const int nchunk = (int)min((int64_t)NCHUNK, (p.odim[AY] - y0 + CHUNK_ROWS - 1) / CHUNK_ROWS);
 
-    for (int m = 0; m < EDF_FAST_M; ++m) {
-        int64_t o[NAXIS];
-        o[AX] = x;
-        if (NAXIS == 3) {
-            o[0] = z0 + g;
-            o[AY] = y0 + m;
-            if (o[0] >= p.odim[0] || o[AY] >= p.odim[AY]) continue;
-        } else {
-            o[AY] = y0 + g * EDF_FAST_M + m;
-            if (o[AY] >= p.odim[AY]) continue;
+    edf_fast_chunk_setup<NAXIS>(s, 0, 0);
+    __syncthreads();
+    for (int c = 0; c < nchunk; ++c) {
+        const int buf = c & 1;
+        if (c + 1 < nchunk) edf_fast_chunk_setup<NAXIS>(s, c + 1, buf ^ 1);   // overlaps with the voxel loop
+        if (xok) {
+            for (int m = 0; m < EDF_FAST_M; ++m) {
+                int64_t o[NAXIS];
+                o[AX] = x;
+                if (NAXIS == 3) {
+                    o[0] = z0 + g;
+                    o[AY] = y0 + c * CHUNK_ROWS + m;
+                    if (o[0] >= p.odim[0] || o[AY] >= p.odim[AY]) continue;
+                } else {
+                    o[AY] = y0 + c * CHUNK_ROWS + g * EDF_FAST_M + m;
+                    if (o[AY] >= p.odim[AY]) continue;
+                }
+                double in[NAXIS];
+                edf_fast_voxel_coords<NAXIS>(p, s, buf, o, g, m, wx, sxrel, in);
+                body(o, in);
+            }
         }
-        double in[NAXIS];
-        edf_fast_voxel_coords<NAXIS>(p, s, o, g, m, tx, wx, sxrel, in);
+        __syncthreads();
+    }
+}
 
+// ---------------------------------------------------------------------------------------
+// float32 kernel: forward gather (GRAD=false) or gradient scatter (GRAD=true)
+// ---------------------------------------------------------------------------------------
+template <int NAXIS, int ORDER, bool GRAD>
+struct EdfFastF32Body {
+    const EdfParams& p;
+    const EdfFastLaunch& L;
+    static constexpr int NT = ORDER + 1;
+
+    __device__ __forceinline__ void operator()(const int64_t* o, const double* in) const
+    {
         for (int ii = 0; ii < p.ninputs; ++ii) {
             if (!((L.input_mask >> ii) & 1u)) continue;
             const EdfInputDesc& d = p.inp[ii];
@@ -295,6 +341,15 @@ edf_fast_f32_kernel(const __grid_constant__ EdfParams p, const __grid_constant__
             }
         }
     }
+};
+
+template <int NAXIS, int ORDER, bool GRAD>
+__global__ void __launch_bounds__(EDF_FAST_THREADS, 2)
+edf_fast_f32_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L)
+{
+    __shared__ EdfFastSmem<NAXIS> s;
+    EdfFastF32Body<NAXIS, ORDER, GRAD> body{p, L};
+    edf_fast_walk_tile<NAXIS>(p, s, body);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -302,39 +357,12 @@ edf_fast_f32_kernel(const __grid_constant__ EdfParams p, const __grid_constant__
 // voxel (label volumes, BASELINE config 3's int32 input) or the converted cval
 // ---------------------------------------------------------------------------------------
 template <int NAXIS, typename T>
-__global__ void __launch_bounds__(EDF_FAST_THREADS)
-edf_fast_copy_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L)
-{
-    __shared__ EdfFastSmem<NAXIS> s;
-    constexpr int AX = NAXIS - 1, AY = NAXIS - 2;
-    const int64_t x0 = (int64_t)blockIdx.x * EDF_FAST_TX;
-    const int64_t y0 = (int64_t)blockIdx.y * EdfFastSmem<NAXIS>::NROWS;
-    const int64_t z0 = (int64_t)blockIdx.z * EDF_FAST_G;
-    edf_fast_tile_setup<NAXIS>(p, s, z0, y0, x0);
+struct EdfFastCopyBody {
+    const EdfParams& p;
+    const EdfFastLaunch& L;
 
-    const int tx = threadIdx.x & (EDF_FAST_TX - 1);
-    const int g = threadIdx.x >> 6;
-    const int64_t x = x0 + tx;
-    if (x >= p.odim[AX]) return;
-    double wx[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) wx[k] = s.wx[tx][k];
-    const int sxrel = s.sx[tx] - s.sx[0];
-
-    for (int m = 0; m < EDF_FAST_M; ++m) {
-        int64_t o[NAXIS];
-        o[AX] = x;
-        if (NAXIS == 3) {
-            o[0] = z0 + g;
-            o[AY] = y0 + m;
-            if (o[0] >= p.odim[0] || o[AY] >= p.odim[AY]) continue;
-        } else {
-            o[AY] = y0 + g * EDF_FAST_M + m;
-            if (o[AY] >= p.odim[AY]) continue;
-        }
-        double in[NAXIS];
-        edf_fast_voxel_coords<NAXIS>(p, s, o, g, m, tx, wx, sxrel, in);
-
+    __device__ __forceinline__ void operator()(const int64_t* o, const double* in) const
+    {
         for (int ii = 0; ii < p.ninputs; ++ii) {
             if (!((L.input_mask >> ii) & 1u)) continue;
             const EdfInputDesc& d = p.inp[ii];
@@ -368,6 +396,15 @@ edf_fast_copy_kernel(const __grid_constant__ EdfParams p, const __grid_constant_
             }
         }
     }
+};
+
+template <int NAXIS, typename T>
+__global__ void __launch_bounds__(EDF_FAST_THREADS, 2)
+edf_fast_copy_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L)
+{
+    __shared__ EdfFastSmem<NAXIS> s;
+    EdfFastCopyBody<NAXIS, T> body{p, L};
+    edf_fast_walk_tile<NAXIS>(p, s, body);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -459,7 +496,7 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
     }
     if (p.ddtype != EDF_F64 && p.ddtype != EDF_F32) return 0;
     if (!edf_fast_ctrl_span_ok(p, AX, EDF_FAST_TX)) return 0;
-    if (!edf_fast_ctrl_span_ok(p, AY, p.naxis == 3 ? EDF_FAST_M : EDF_FAST_G * EDF_FAST_M)) return 0;
+    if (!edf_fast_ctrl_span_ok(p, AY, EDF_FAST_RY)) return 0;
 
     EdfFastLaunch L;
     memset(&L, 0, sizeof(L));
@@ -468,13 +505,8 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
 
     dim3 grid;
     grid.x = (unsigned)((p.odim[AX] + EDF_FAST_TX - 1) / EDF_FAST_TX);
-    if (p.naxis == 3) {
-        grid.y = (unsigned)((p.odim[AY] + EDF_FAST_M - 1) / EDF_FAST_M);
-        grid.z = (unsigned)((p.odim[0] + EDF_FAST_G - 1) / EDF_FAST_G);
-    } else {
-        grid.y = (unsigned)((p.odim[AY] + EDF_FAST_G * EDF_FAST_M - 1) / (EDF_FAST_G * EDF_FAST_M));
-        grid.z = 1;
-    }
+    grid.y = (unsigned)((p.odim[AY] + EDF_FAST_RY - 1) / EDF_FAST_RY);
+    grid.z = (p.naxis == 3) ? (unsigned)((p.odim[0] + EDF_FAST_G - 1) / EDF_FAST_G) : 1u;
     if (grid.y > 65535u || grid.z > 65535u) return 0;
 
     int launches = 0;
