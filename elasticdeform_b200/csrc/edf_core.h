@@ -20,8 +20,12 @@
 #if defined(__CUDACC__)
 #define EDF_HD __host__ __device__ __forceinline__
 #define EDF_D __device__ __forceinline__
+// out-of-line: keeps rarely taken, division-heavy paths from being if-converted /
+// speculated into the hot loop (ptxas hoists pure fp64 divisions above branches)
+#define EDF_COLD __host__ __device__ __noinline__
 #else
 #define EDF_HD static inline
+#define EDF_COLD static __attribute__((noinline))
 #endif
 
 #define EDF_MAX_STEP (EDF_MAX_DIMS - 1)
@@ -71,6 +75,8 @@ struct EdfParams {
     const char* disp;                 // device pointer, prefiltered coefficients
     int32_t ddtype, pad_;
     double  affine[EDF_MAX_AXIS * (EDF_MAX_AXIS + 1)];
+    double  idim_m1[EDF_MAX_AXIS];    // (double)(idim - 1), hoisted int64 -> double conversions
+    double  ooff_d[EDF_MAX_AXIS];     // (double)ooff
     EdfInputDesc inp[EDF_MAX_INPUTS];
 };
 
@@ -144,7 +150,7 @@ EDF_HD void edf_bspline_weights(double x, int order, double* w)
 // coordinate boundary map, reference deform.c:47-128 (pre-1.6 SciPy semantics:
 // wrap has period len-1, reflect maps (-1,0) onto (-1,0), constant -> -1).
 // ----------------------------------------------------------------------------
-EDF_HD double edf_map_coordinate(double in, int64_t len, int mode)
+EDF_COLD double edf_map_coordinate_cold(double in, int64_t len, int mode)
 {
     if (in < 0) {
         switch (mode) {
@@ -221,9 +227,18 @@ EDF_HD double edf_map_coordinate(double in, int64_t len, int mode)
     return in;
 }
 
+// In-range coordinates pass through unchanged and 'constant' needs no arithmetic; everything
+// else takes the out-of-line path above.  Same results as calling the full map directly.
+EDF_HD double edf_map_coordinate(double in, int64_t len, int mode)
+{
+    if (in >= 0.0 && in <= (double)(len - 1)) return in;
+    if (mode == EDF_MODE_CONSTANT) return (in < 0 || in > (double)(len - 1)) ? -1.0 : in;
+    return edf_map_coordinate_cold(in, len, mode);
+}
+
 // Mirror map of a tap index that fell outside [0, len): reference deform.c:669-683
 // and :796-810 (used for EVERY boundary mode, also for the control grid).
-EDF_HD int64_t edf_mirror_index(int64_t idx, int64_t len)
+EDF_COLD int64_t edf_mirror_index_cold(int64_t idx, int64_t len)
 {
     if (len <= 1) return 0;
     const int64_t s2 = 2 * len - 2;
@@ -235,6 +250,12 @@ EDF_HD int64_t edf_mirror_index(int64_t idx, int64_t len)
         if (idx >= len) idx = s2 - idx;
     }
     return idx;
+}
+
+EDF_HD int64_t edf_mirror_index(int64_t idx, int64_t len)
+{
+    if (idx >= 0 && idx < len) return idx;        // the map is the identity inside [0, len)
+    return edf_mirror_index_cold(idx, len);
 }
 
 // ----------------------------------------------------------------------------
@@ -394,8 +415,8 @@ EDF_HD void edf_displacement_exact(const EdfParams& p, const int64_t* o, double*
 
 // Un-mapped source coordinate of output voxel o along axis h for one input
 // (affine, crop offset, displacement): deform.c:771-781 before map_coordinate.
-template <int NAXIS>
-EDF_HD double edf_source_coordinate(const EdfParams& p, const int64_t* o, int h, double displ_h)
+template <int NAXIS, typename I>
+EDF_HD double edf_source_coordinate(const EdfParams& p, const I* o, int h, double displ_h)
 {
     double cc;
     if (p.has_affine) {
@@ -449,7 +470,7 @@ EDF_HD void edf_generic_voxel(const EdfParams& p, int64_t kk)
 #pragma unroll
         for (int h = 0; h < NAXIS; ++h) {
             if (constant) continue;                                // deform.c:819-823 (break)
-            double cc = edf_source_coordinate<NAXIS>(p, o, h, displ[h]);
+            double cc = edf_source_coordinate<NAXIS, int64_t>(p, o, h, displ[h]);
             cc = edf_map_coordinate(cc, p.idim[h], d.mode);
             if (cc > -1.0) {
                 const int64_t start = edf_window_start(cc, order);

@@ -140,16 +140,19 @@ __device__ __forceinline__ void edf_fast_chunk_setup(EdfFastSmem<NAXIS>& s, int 
 // exact reference-order displacement, kept out of line so that its index tables do not
 // inflate the register footprint of the hot loop (it runs for ~1 voxel in 10^6)
 template <int NAXIS>
-__device__ __noinline__ void edf_displacement_exact_cold(const EdfParams& p, const int64_t* o, double* dd)
+__device__ __noinline__ void edf_displacement_exact_cold(const EdfParams& p, const int* o, double* dd)
 {
-    edf_displacement_exact<NAXIS>(p, o, dd);
+    int64_t o64[NAXIS];
+#pragma unroll
+    for (int h = 0; h < NAXIS; ++h) o64[h] = o[h];
+    edf_displacement_exact<NAXIS>(p, o64, dd);
 }
 
 // un-mapped source coordinates in[h] of one voxel, with the exact-order re-evaluation
 // of the voxels that sit next to a discontinuity
 template <int NAXIS>
 __device__ __forceinline__ void edf_fast_voxel_coords(const EdfParams& p, const EdfFastSmem<NAXIS>& s,
-                                                      int buf, const int64_t* o, int g, int m,
+                                                      int buf, const int* o, int g, int m,
                                                       const double* wx, int sxrel, double* in)
 {
     bool danger = false;
@@ -158,28 +161,30 @@ __device__ __forceinline__ void edf_fast_voxel_coords(const EdfParams& p, const 
         double d = 0.0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) d = fma(s.B[buf][h][g][m][sxrel + k], wx[k], d);
-        in[h] = edf_source_coordinate<NAXIS>(p, o, h, d);
+        if (p.has_affine) in[h] = edf_source_coordinate<NAXIS, int>(p, o, h, d);
+        else              in[h] = xadd(xadd((double)o[h], p.ooff_d[h]), d);     // deform.c:778-781
         danger |= edf_near_half_integer(in[h]);
     }
     if (danger && s.nonzero) {
         double dd[NAXIS];
         edf_displacement_exact_cold<NAXIS>(p, o, dd);
 #pragma unroll
-        for (int h = 0; h < NAXIS; ++h) in[h] = edf_source_coordinate<NAXIS>(p, o, h, dd[h]);
+        for (int h = 0; h < NAXIS; ++h) in[h] = edf_source_coordinate<NAXIS, int>(p, o, h, dd[h]);
     }
 }
 
 // per-axis tap offsets (element units) with the reference's mirror edge mapping
 template <int ORDER>
-__device__ __forceinline__ void edf_fast_tap_offsets(int start, int len, int stride_e, int* off)
+__device__ __forceinline__ bool edf_fast_tap_offsets(int start, int len, int stride_e, int* off)
 {
     const bool edge = start < 0 || start + ORDER >= len;
 #pragma unroll
     for (int l = 0; l <= ORDER; ++l) {
         int idx = start + l;
-        if (edge) idx = (int)edf_mirror_index(idx, len);
+        if (edge) idx = edf_mirror_index32(idx, len);
         off[l] = idx * stride_e;
     }
+    return edge;
 }
 
 // Tile walker shared by all fast kernels: calls body(o, in) for every output voxel of the CTA's
@@ -212,15 +217,15 @@ __device__ __forceinline__ void edf_fast_walk_tile(const EdfParams& p, EdfFastSm
         if (c + 1 < nchunk) edf_fast_chunk_setup<NAXIS>(s, c + 1, buf ^ 1);   // overlaps with the voxel loop
         if (xok) {
             for (int m = 0; m < EDF_FAST_M; ++m) {
-                int64_t o[NAXIS];
-                o[AX] = x;
+                int o[NAXIS];
+                o[AX] = (int)x;
                 if (NAXIS == 3) {
-                    o[0] = z0 + g;
-                    o[AY] = y0 + c * CHUNK_ROWS + m;
-                    if (o[0] >= p.odim[0] || o[AY] >= p.odim[AY]) continue;
+                    o[0] = (int)z0 + g;
+                    o[AY] = (int)y0 + c * CHUNK_ROWS + m;
+                    if (o[0] >= (int)p.odim[0] || o[AY] >= (int)p.odim[AY]) continue;
                 } else {
-                    o[AY] = y0 + c * CHUNK_ROWS + g * EDF_FAST_M + m;
-                    if (o[AY] >= p.odim[AY]) continue;
+                    o[AY] = (int)y0 + c * CHUNK_ROWS + g * EDF_FAST_M + m;
+                    if (o[AY] >= (int)p.odim[AY]) continue;
                 }
                 double in[NAXIS];
                 edf_fast_voxel_coords<NAXIS>(p, s, buf, o, g, m, wx, sxrel, in);
@@ -240,12 +245,12 @@ struct EdfFastF32Body {
     const EdfFastLaunch& L;
     static constexpr int NT = ORDER + 1;
 
-    __device__ __forceinline__ void operator()(const int64_t* o, const double* in) const
+    __device__ __forceinline__ void operator()(const int* o, const double* in) const
     {
         for (int ii = 0; ii < p.ninputs; ++ii) {
             if (!((L.input_mask >> ii) & 1u)) continue;
             const EdfInputDesc& d = p.inp[ii];
-            bool constant = false;
+            bool constant = false, edge = false;
             float w[NAXIS][NT];
             int off[NAXIS][NT];
 #pragma unroll
@@ -254,21 +259,31 @@ struct EdfFastF32Body {
                 float fr = 0.f;
                 if (!constant && !edf_fast_finish(p, d.mode, ORDER, h, in[h], &st, &fr)) constant = true;
                 if (!constant) {
-                    edf_fast_tap_offsets<ORDER>(st, (int)p.idim[h], L.istr_e[ii][h], off[h]);
+                    edge |= edf_fast_tap_offsets<ORDER>(st, (int)p.idim[h], L.istr_e[ii][h], off[h]);
                     if (ORDER > 0) edf_bspline_weights_f32<ORDER>(fr, w[h]);
                 }
             }
             int64_t obase = 0;
 #pragma unroll
-            for (int h = 0; h < NAXIS; ++h) obase += o[h] * (int64_t)L.ostr_e[ii][h];
+            for (int h = 0; h < NAXIS; ++h) obase += (int64_t)o[h] * L.ostr_e[ii][h];
+            // interior voxels on a unit-stride last axis: taps are base + i*sz + j*sy + k
+            const bool dense = !edge && L.istr_e[ii][NAXIS - 1] == 1;
+            const int sz_e = L.istr_e[ii][0], sy_e = (NAXIS == 3) ? L.istr_e[ii][1] : 0;
 
-            for (int64_t ss = 0; ss < d.nsteps; ++ss) {
-                int64_t istep = 0, ostep = 0, r = ss;
-                for (int q = 0; q < d.nstep_rank; ++q) {
-                    const int64_t c = r % d.step_dim[q];
-                    r /= d.step_dim[q];
-                    istep += d.in_step_str[q] * c;
-                    ostep += d.out_step_str[q] * c;
+            const int64_t nsteps = d.nsteps;
+            for (int64_t ss = 0; ss < nsteps; ++ss) {
+                int64_t istep = 0, ostep = 0;
+                if (d.nstep_rank == 1) {
+                    istep = d.in_step_str[0] * ss;
+                    ostep = d.out_step_str[0] * ss;
+                } else if (d.nstep_rank > 1) {
+                    int64_t r = ss;
+                    for (int q = 0; q < d.nstep_rank; ++q) {
+                        const int64_t c = r % d.step_dim[q];
+                        r /= d.step_dim[q];
+                        istep += d.in_step_str[q] * c;
+                        ostep += d.out_step_str[q] * c;
+                    }
                 }
                 float* po = (float*)(d.out + ostep) + obase;
                 if (!GRAD) {
@@ -281,6 +296,37 @@ struct EdfFastF32Body {
 #pragma unroll
                         for (int h = 0; h < NAXIS; ++h) e += off[h][0];
                         t = __ldg(pi + e);
+                    } else if (dense) {
+                        int e0 = 0;
+#pragma unroll
+                        for (int h = 0; h < NAXIS; ++h) e0 += off[h][0];
+                        const float* base = pi + e0;
+                        t = 0.f;
+                        if (NAXIS == 3) {
+#pragma unroll
+                            for (int i = 0; i < NT; ++i) {
+                                const float* pz = base + (int64_t)i * sz_e;
+                                float ti = 0.f;
+#pragma unroll
+                                for (int j = 0; j < NT; ++j) {
+                                    const float* row = pz + (int64_t)j * sy_e;
+                                    float tj = 0.f;
+#pragma unroll
+                                    for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + k), w[2][k], tj);
+                                    ti = fmaf(tj, w[1][j], ti);
+                                }
+                                t = fmaf(ti, w[0][i], t);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) {
+                                const float* row = base + (int64_t)j * sz_e;
+                                float tj = 0.f;
+#pragma unroll
+                                for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + k), w[1][k], tj);
+                                t = fmaf(tj, w[0][j], t);
+                            }
+                        }
                     } else if (NAXIS == 3) {
                         t = 0.f;
 #pragma unroll
@@ -361,7 +407,7 @@ struct EdfFastCopyBody {
     const EdfParams& p;
     const EdfFastLaunch& L;
 
-    __device__ __forceinline__ void operator()(const int64_t* o, const double* in) const
+    __device__ __forceinline__ void operator()(const int* o, const double* in) const
     {
         for (int ii = 0; ii < p.ninputs; ++ii) {
             if (!((L.input_mask >> ii) & 1u)) continue;
@@ -380,7 +426,7 @@ struct EdfFastCopyBody {
             }
             int64_t obase = 0;
 #pragma unroll
-            for (int h = 0; h < NAXIS; ++h) obase += o[h] * (int64_t)L.ostr_e[ii][h];
+            for (int h = 0; h < NAXIS; ++h) obase += (int64_t)o[h] * L.ostr_e[ii][h];
             for (int64_t ss = 0; ss < d.nsteps; ++ss) {
                 int64_t istep = 0, ostep = 0, r = ss;
                 for (int q = 0; q < d.nstep_rank; ++q) {

@@ -28,8 +28,11 @@
 
 EDF_HD bool edf_near_half_integer(double v)
 {
-    const double t = v + v;
-    return fabs(t - rint(t)) < 2.0 * EDF_FAST_EPS;
+    // distance of 2v to the nearest integer via the 1.5*2^52 rounding trick (two fp64 adds
+    // instead of a conversion-unit rint); valid for |v| < 2^50
+    const double t = xadd(v, v);
+    const double r = xsub(xadd(t, 6755399441055744.0), 6755399441055744.0);
+    return fabs(xsub(t, r)) < 2.0 * EDF_FAST_EPS;
 }
 
 // control-grid table entry of output index o on axis a: window start + 4 weights
@@ -57,7 +60,11 @@ EDF_HD bool edf_fast_ctrl_span_ok(const EdfParams& p, int a, int T)
 EDF_HD bool edf_fast_finish(const EdfParams& p, int mode, int order, int h, double in,
                             int* start, float* frac)
 {
-    const double cc = edf_map_coordinate(in, p.idim[h], mode);
+    double cc = in;
+    if (!(in >= 0.0 && in <= p.idim_m1[h])) {               // same map as edf_map_coordinate
+        if (mode == EDF_MODE_CONSTANT) cc = (in < 0 || in > p.idim_m1[h]) ? -1.0 : in;
+        else cc = edf_map_coordinate_cold(in, p.idim[h], mode);
+    }
     if (!(cc > -1.0)) return false;
     const double fl = (order & 1) ? floor(cc) : floor(xadd(cc, 0.5));
     *start = (int)fl - order / 2;
@@ -182,12 +189,12 @@ static int edf_fast_coords_host_n(const EdfParams& p, int ii, int64_t* starts, f
                 double s = 0.0;
                 for (int k = 0; k < 4; ++k) s = fma(B[h][t][ty][sx[tx] - sx_min + k], wx[tx][k], s);
                 dd[h] = s;
-                in[h] = edf_source_coordinate<NAXIS>(p, o, h, dd[h]);
+                in[h] = edf_source_coordinate<NAXIS, int64_t>(p, o, h, dd[h]);
                 if (edf_near_half_integer(in[h])) danger = true;
             }
             if (danger && !allzero) {
                 edf_displacement_exact<NAXIS>(p, o, dd);
-                for (int h = 0; h < NAXIS; ++h) in[h] = edf_source_coordinate<NAXIS>(p, o, h, dd[h]);
+                for (int h = 0; h < NAXIS; ++h) in[h] = edf_source_coordinate<NAXIS, int64_t>(p, o, h, dd[h]);
                 ++*n_exact;
             }
             int64_t kk = 0;

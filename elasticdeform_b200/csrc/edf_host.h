@@ -117,6 +117,8 @@ static int flatten_problem(const edf_problem* pr, int gradient, EdfParams& p)
         p.idim[j] = pr->inputs[0].shape[pr->axis[j]];
         p.odim[j] = pr->outputs[0].shape[pr->axis[j]];
         p.ooff[j] = pr->output_offset ? pr->output_offset[j] : 0;
+        p.idim_m1[j] = (double)(p.idim[j] - 1);
+        p.ooff_d[j] = (double)p.ooff[j];
         p.size *= p.odim[j];
     }
     const edf_array& D = pr->displacement;

@@ -87,7 +87,7 @@ static void exact_coords_n(const EdfParams& p, int ii, int64_t* starts, float* f
         bool cst = false;
         for (int h = 0; h < NAXIS; ++h) {
             int st = 0; float fr = 0.f;
-            const double in = edf_source_coordinate<NAXIS>(p, o, h, dd[h]);
+            const double in = edf_source_coordinate<NAXIS, int64_t>(p, o, h, dd[h]);
             if (!cst && !edf_fast_finish(p, d.mode, d.order, h, in, &st, &fr)) cst = true;
             starts[kk * NAXIS + h] = cst ? 0 : st;
             fracs[kk * NAXIS + h] = cst ? 0.f : fr;
