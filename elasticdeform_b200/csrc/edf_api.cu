@@ -13,6 +13,7 @@
 #include "edf_spline_lines.h"
 #include "edf_host.h"
 #include "edf_fast.cuh"
+#include "edf_lean.cuh"
 
 // ----------------------------------------------------------------------------
 // error plumbing

@@ -239,152 +239,161 @@ __device__ __forceinline__ void edf_fast_walk_tile(const EdfParams& p, EdfFastSm
 // ---------------------------------------------------------------------------------------
 // float32 kernel: forward gather (GRAD=false) or gradient scatter (GRAD=true)
 // ---------------------------------------------------------------------------------------
+// all the work for one float32 input at one output voxel (general path: any mode, edges, strides,
+// non-deformed "step" axes)
+template <int NAXIS, int ORDER, bool GRAD>
+__device__ __forceinline__ void edf_fast_f32_one_input(const EdfParams& p, const EdfFastLaunch& L, int ii,
+                                                       const int* o, const double* in)
+{
+    constexpr int NT = ORDER + 1;
+    const EdfInputDesc& d = p.inp[ii];
+    bool constant = false, edge = false;
+    float w[NAXIS][NT];
+    int off[NAXIS][NT];
+#pragma unroll
+    for (int h = 0; h < NAXIS; ++h) {
+        int st = 0;
+        float fr = 0.f;
+        if (!constant && !edf_fast_finish(p, d.mode, ORDER, h, in[h], &st, &fr)) constant = true;
+        if (!constant) {
+            edge |= edf_fast_tap_offsets<ORDER>(st, (int)p.idim[h], L.istr_e[ii][h], off[h]);
+            if (ORDER > 0) edf_bspline_weights_f32<ORDER>(fr, w[h]);
+        }
+    }
+    int64_t obase = 0;
+#pragma unroll
+    for (int h = 0; h < NAXIS; ++h) obase += (int64_t)o[h] * L.ostr_e[ii][h];
+    // interior voxels on a unit-stride last axis: taps are base + i*sz + j*sy + k
+    const bool dense = !edge && L.istr_e[ii][NAXIS - 1] == 1;
+    const int sz_e = L.istr_e[ii][0], sy_e = (NAXIS == 3) ? L.istr_e[ii][1] : 0;
+
+    const int64_t nsteps = d.nsteps;
+    for (int64_t ss = 0; ss < nsteps; ++ss) {
+        int64_t istep = 0, ostep = 0;
+        if (d.nstep_rank == 1) {
+            istep = d.in_step_str[0] * ss;
+            ostep = d.out_step_str[0] * ss;
+        } else if (d.nstep_rank > 1) {
+            int64_t r = ss;
+            for (int q = 0; q < d.nstep_rank; ++q) {
+                const int64_t c = r % d.step_dim[q];
+                r /= d.step_dim[q];
+                istep += d.in_step_str[q] * c;
+                ostep += d.out_step_str[q] * c;
+            }
+        }
+        float* po = (float*)(d.out + ostep) + obase;
+        if (!GRAD) {
+            const float* __restrict__ pi = (const float*)(d.in + istep);
+            float t;
+            if (constant) {
+                t = __uint_as_float((uint32_t)L.cval_bits[ii]);
+            } else if (ORDER == 0) {
+                int e = 0;
+#pragma unroll
+                for (int h = 0; h < NAXIS; ++h) e += off[h][0];
+                t = __ldg(pi + e);
+            } else if (dense) {
+                int e0 = 0;
+#pragma unroll
+                for (int h = 0; h < NAXIS; ++h) e0 += off[h][0];
+                const float* base = pi + e0;
+                t = 0.f;
+                if (NAXIS == 3) {
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) {
+                        const float* pz = base + (int64_t)i * sz_e;
+                        float ti = 0.f;
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            const float* row = pz + (int64_t)j * sy_e;
+                            float tj = 0.f;
+#pragma unroll
+                            for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + k), w[2][k], tj);
+                            ti = fmaf(tj, w[1][j], ti);
+                        }
+                        t = fmaf(ti, w[0][i], t);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const float* row = base + (int64_t)j * sz_e;
+                        float tj = 0.f;
+#pragma unroll
+                        for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + k), w[1][k], tj);
+                        t = fmaf(tj, w[0][j], t);
+                    }
+                }
+            } else if (NAXIS == 3) {
+                t = 0.f;
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+                    float ti = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const float* row = pi + (off[0][i] + off[1][j]);
+                        float tj = 0.f;
+#pragma unroll
+                        for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + off[2][k]), w[2][k], tj);
+                        ti = fmaf(tj, w[1][j], ti);
+                    }
+                    t = fmaf(ti, w[0][i], t);
+                }
+            } else {
+                t = 0.f;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const float* row = pi + off[0][j];
+                    float tj = 0.f;
+#pragma unroll
+                    for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + off[1][k]), w[1][k], tj);
+                    t = fmaf(tj, w[0][j], t);
+                }
+            }
+            *po = t;
+        } else if (!constant) {
+            float* pi = (float*)(d.in + istep);
+            const float gval = *po;
+            if (ORDER == 0) {
+                int e = 0;
+#pragma unroll
+                for (int h = 0; h < NAXIS; ++h) e += off[h][0];
+                atomicAdd(pi + e, gval);
+            } else if (NAXIS == 3) {
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+                    const float gi = gval * w[0][i];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const float gj = gi * w[1][j];
+                        float* row = pi + (off[0][i] + off[1][j]);
+#pragma unroll
+                        for (int k = 0; k < NT; ++k) atomicAdd(row + off[2][k], gj * w[2][k]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const float gj = gval * w[0][j];
+                    float* row = pi + off[0][j];
+#pragma unroll
+                    for (int k = 0; k < NT; ++k) atomicAdd(row + off[1][k], gj * w[1][k]);
+                }
+            }
+        }
+    }
+}
+
 template <int NAXIS, int ORDER, bool GRAD>
 struct EdfFastF32Body {
     const EdfParams& p;
     const EdfFastLaunch& L;
-    static constexpr int NT = ORDER + 1;
 
     __device__ __forceinline__ void operator()(const int* o, const double* in) const
     {
         for (int ii = 0; ii < p.ninputs; ++ii) {
             if (!((L.input_mask >> ii) & 1u)) continue;
-            const EdfInputDesc& d = p.inp[ii];
-            bool constant = false, edge = false;
-            float w[NAXIS][NT];
-            int off[NAXIS][NT];
-#pragma unroll
-            for (int h = 0; h < NAXIS; ++h) {
-                int st = 0;
-                float fr = 0.f;
-                if (!constant && !edf_fast_finish(p, d.mode, ORDER, h, in[h], &st, &fr)) constant = true;
-                if (!constant) {
-                    edge |= edf_fast_tap_offsets<ORDER>(st, (int)p.idim[h], L.istr_e[ii][h], off[h]);
-                    if (ORDER > 0) edf_bspline_weights_f32<ORDER>(fr, w[h]);
-                }
-            }
-            int64_t obase = 0;
-#pragma unroll
-            for (int h = 0; h < NAXIS; ++h) obase += (int64_t)o[h] * L.ostr_e[ii][h];
-            // interior voxels on a unit-stride last axis: taps are base + i*sz + j*sy + k
-            const bool dense = !edge && L.istr_e[ii][NAXIS - 1] == 1;
-            const int sz_e = L.istr_e[ii][0], sy_e = (NAXIS == 3) ? L.istr_e[ii][1] : 0;
-
-            const int64_t nsteps = d.nsteps;
-            for (int64_t ss = 0; ss < nsteps; ++ss) {
-                int64_t istep = 0, ostep = 0;
-                if (d.nstep_rank == 1) {
-                    istep = d.in_step_str[0] * ss;
-                    ostep = d.out_step_str[0] * ss;
-                } else if (d.nstep_rank > 1) {
-                    int64_t r = ss;
-                    for (int q = 0; q < d.nstep_rank; ++q) {
-                        const int64_t c = r % d.step_dim[q];
-                        r /= d.step_dim[q];
-                        istep += d.in_step_str[q] * c;
-                        ostep += d.out_step_str[q] * c;
-                    }
-                }
-                float* po = (float*)(d.out + ostep) + obase;
-                if (!GRAD) {
-                    const float* __restrict__ pi = (const float*)(d.in + istep);
-                    float t;
-                    if (constant) {
-                        t = __uint_as_float((uint32_t)L.cval_bits[ii]);
-                    } else if (ORDER == 0) {
-                        int e = 0;
-#pragma unroll
-                        for (int h = 0; h < NAXIS; ++h) e += off[h][0];
-                        t = __ldg(pi + e);
-                    } else if (dense) {
-                        int e0 = 0;
-#pragma unroll
-                        for (int h = 0; h < NAXIS; ++h) e0 += off[h][0];
-                        const float* base = pi + e0;
-                        t = 0.f;
-                        if (NAXIS == 3) {
-#pragma unroll
-                            for (int i = 0; i < NT; ++i) {
-                                const float* pz = base + (int64_t)i * sz_e;
-                                float ti = 0.f;
-#pragma unroll
-                                for (int j = 0; j < NT; ++j) {
-                                    const float* row = pz + (int64_t)j * sy_e;
-                                    float tj = 0.f;
-#pragma unroll
-                                    for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + k), w[2][k], tj);
-                                    ti = fmaf(tj, w[1][j], ti);
-                                }
-                                t = fmaf(ti, w[0][i], t);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < NT; ++j) {
-                                const float* row = base + (int64_t)j * sz_e;
-                                float tj = 0.f;
-#pragma unroll
-                                for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + k), w[1][k], tj);
-                                t = fmaf(tj, w[0][j], t);
-                            }
-                        }
-                    } else if (NAXIS == 3) {
-                        t = 0.f;
-#pragma unroll
-                        for (int i = 0; i < NT; ++i) {
-                            float ti = 0.f;
-#pragma unroll
-                            for (int j = 0; j < NT; ++j) {
-                                const float* row = pi + (off[0][i] + off[1][j]);
-                                float tj = 0.f;
-#pragma unroll
-                                for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + off[2][k]), w[2][k], tj);
-                                ti = fmaf(tj, w[1][j], ti);
-                            }
-                            t = fmaf(ti, w[0][i], t);
-                        }
-                    } else {
-                        t = 0.f;
-#pragma unroll
-                        for (int j = 0; j < NT; ++j) {
-                            const float* row = pi + off[0][j];
-                            float tj = 0.f;
-#pragma unroll
-                            for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + off[1][k]), w[1][k], tj);
-                            t = fmaf(tj, w[0][j], t);
-                        }
-                    }
-                    *po = t;
-                } else if (!constant) {
-                    float* pi = (float*)(d.in + istep);
-                    const float gval = *po;
-                    if (ORDER == 0) {
-                        int e = 0;
-#pragma unroll
-                        for (int h = 0; h < NAXIS; ++h) e += off[h][0];
-                        atomicAdd(pi + e, gval);
-                    } else if (NAXIS == 3) {
-#pragma unroll
-                        for (int i = 0; i < NT; ++i) {
-                            const float gi = gval * w[0][i];
-#pragma unroll
-                            for (int j = 0; j < NT; ++j) {
-                                const float gj = gi * w[1][j];
-                                float* row = pi + (off[0][i] + off[1][j]);
-#pragma unroll
-                                for (int k = 0; k < NT; ++k) atomicAdd(row + off[2][k], gj * w[2][k]);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < NT; ++j) {
-                            const float gj = gval * w[0][j];
-                            float* row = pi + off[0][j];
-#pragma unroll
-                            for (int k = 0; k < NT; ++k) atomicAdd(row + off[1][k], gj * w[1][k]);
-                        }
-                    }
-                }
-            }
+            edf_fast_f32_one_input<NAXIS, ORDER, GRAD>(p, L, ii, o, in);
         }
     }
 };
@@ -527,6 +536,11 @@ static void edf_fast_launch_copy(int es, dim3 grid, cudaStream_t st, const EdfPa
     }
 }
 
+// straight-line 3-D float32 kernels (edf_lean.cuh)
+static bool edf_lean_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii);
+static void edf_lean_launch(int order, int gradient, dim3 grid, cudaStream_t st, const EdfParams& p,
+                            const EdfFastLaunch& L, int ii);
+
 // Tries to run (part of) the problem on the specialised kernels.
 //   *handled_mask receives the inputs that were processed (the caller runs the generic
 //   kernel for the others); returns the number of kernels launched, or <0 on a launch error.
@@ -559,6 +573,17 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
     bool done[EDF_MAX_INPUTS] = {false};
     for (int ii = 0; ii < p.ninputs; ++ii) {
         if (done[ii] || cls[ii] == EDF_CLASS_NONE) continue;
+        if (cls[ii] == EDF_CLASS_F32 && edf_lean_eligible(p, L, ii)) {
+            L.input_mask = 1u << ii;
+            edf_lean_launch(p.inp[ii].order, p.gradient, grid, st, p, L, ii);
+            g_fast_launch_error = cudaGetLastError();
+            if (g_fast_launch_error != cudaSuccess) return -1;
+            *name = p.gradient ? "lean3d_f32_grad" : "lean3d_f32";
+            done[ii] = true;
+            ++launches;
+            *handled_mask |= 1u << ii;
+            continue;
+        }
         // group every later input with the same class / order / element size
         uint32_t mask = 0;
         const int es = edf_elem_size(p.inp[ii].in_dtype);

@@ -1,0 +1,331 @@
+// edf_lean.cuh -- straight-line 3-D float32 kernels for the headline configuration:
+// one float32 volume, unit-stride last axis, no non-deformed axes, any order/mode.
+//
+// Same tile geometry and coordinate pipeline as edf_fast.cuh (tables A/B in shared memory, 12
+// fp64 FMAs per voxel), but the common case -- a voxel whose whole tap window lies inside the
+// volume and whose coordinates are not next to a rounding threshold -- runs branch-free:
+//   3 x (floor, frac, start)  ->  fp32 weights  ->  16 row pointers by 64-bit adds  ->
+//   (order+1)^3 loads with immediate offsets  ->  fp32 FMAs  ->  one coalesced store.
+// Everything else (edges, out-of-range coordinates in a non-constant mode, voxels within 1e-6 of
+// a threshold, which are re-evaluated in the reference order) goes through the out-of-line
+// general routine of edf_fast.cuh, so results are identical to the general fast kernel.
+#pragma once
+#include "edf_fast.cuh"
+#include <stdlib.h>
+
+#define EDF_LEAN_EPSF 1e-6f        // float-side threshold test; superset of EDF_FAST_EPS (2e-8)
+
+// shared-memory tables of the lean kernels: like EdfFastSmem, but the y-contraction B is
+// private to each warp (a warp owns one slab g and 32 x positions), so the main loop needs no
+// CTA-wide barrier and warps with little work (outside the volume) do not hold the others up.
+struct EdfLeanSmem {
+    double wz[EDF_FAST_G][4];
+    double wy[EDF_FAST_RY][4];
+    double wx[EDF_FAST_TX][4];
+    int    sz[EDF_FAST_G];
+    int    sy[EDF_FAST_RY];
+    int    sx[EDF_FAST_TX];
+    int    ny, nx, nonzero, pad_;
+    double A[3][EDF_FAST_G][EDF_FAST_NC][EDF_FAST_NC];
+    double Bw[EDF_FAST_THREADS / 32][3][EDF_FAST_M][EDF_FAST_NC];
+};
+
+__device__ __forceinline__ void edf_lean_tile_setup(const EdfParams& p, EdfLeanSmem& s, int z0, int y0, int x0)
+{
+    const int tid = threadIdx.x;
+    if (tid == 0) s.nonzero = 0;
+    if (tid < EDF_FAST_TX) {
+        edf_fast_ctrl_entry(p, 2, min((int64_t)(x0 + tid), p.odim[2] - 1), s.wx[tid], &s.sx[tid]);
+    } else if (tid < EDF_FAST_TX + EDF_FAST_RY) {
+        const int t = tid - EDF_FAST_TX;
+        edf_fast_ctrl_entry(p, 1, min((int64_t)(y0 + t), p.odim[1] - 1), s.wy[t], &s.sy[t]);
+    } else if (tid < EDF_FAST_TX + EDF_FAST_RY + EDF_FAST_G) {
+        const int t = tid - EDF_FAST_TX - EDF_FAST_RY;
+        edf_fast_ctrl_entry(p, 0, min((int64_t)(z0 + t), p.odim[0] - 1), s.wz[t], &s.sz[t]);
+    }
+    __syncthreads();
+    const int sy_min = s.sy[0], sx_min = s.sx[0];
+    const int ny = s.sy[EDF_FAST_RY - 1] - sy_min + 4;
+    const int nx = s.sx[EDF_FAST_TX - 1] - sx_min + 4;
+    if (tid == 0) { s.ny = ny; s.nx = nx; }
+    bool nz = false;
+    const int na = 3 * EDF_FAST_G * ny * nx;
+    for (int e = tid; e < na; e += EDF_FAST_THREADS) {
+        const int jx = e % nx;
+        const int jy = (e / nx) % ny;
+        const int t = (e / (nx * ny)) % EDF_FAST_G;
+        const int h = e / (nx * ny * EDF_FAST_G);
+        const int my = edf_mirror_index32(sy_min + jy, (int)p.ncp[1]);
+        const int mx = edf_mirror_index32(sx_min + jx, (int)p.ncp[2]);
+        const char* base = p.disp + p.dstr[0] * h + my * p.dstr[2] + mx * p.dstr[3];
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int mz = edf_mirror_index32(s.sz[t] + i, (int)p.ncp[0]);
+            const double c = (p.ddtype == EDF_F64) ? *(const double*)(base + mz * p.dstr[1])
+                                                   : (double)*(const float*)(base + mz * p.dstr[1]);
+            nz |= (c != 0.0);
+            a = fma(c, s.wz[t][i], a);
+        }
+        s.A[h][t][jy][jx] = a;
+    }
+    if (nz) s.nonzero = 1;
+    __syncthreads();
+}
+
+// exact reference-order re-evaluation of one voxel's un-mapped coordinates (cold)
+__device__ __noinline__ void edf_lean_exact_coords(const EdfParams& p, int z, int y, int x,
+                                                   double* inz, double* iny, double* inx)
+{
+    int o[3] = {z, y, x};
+    double dd[3];
+    edf_displacement_exact_cold<3>(p, o, dd);
+    *inz = edf_source_coordinate<3, int>(p, o, 0, dd[0]);
+    *iny = edf_source_coordinate<3, int>(p, o, 1, dd[1]);
+    *inx = edf_source_coordinate<3, int>(p, o, 2, dd[2]);
+}
+
+// One axis of one voxel: boundary map (only out-of-range coordinates leave the inline path),
+// floor / fractional offset / window start, and the "next to a threshold" tests.
+// Returns true when the voxel takes the constant value (deform.c:782, :819-823).
+template <int ORDER>
+__device__ __forceinline__ bool edf_lean_axis(const EdfParams& p, int h, int mode, double in, double lim,
+                                              bool gate, int& start, float& frac, bool& danger)
+{
+    double cc = in;
+    if (!((in >= 0.0) & (in <= lim))) {
+        if (mode == EDF_MODE_CONSTANT) {
+            // misses the volume: constant, unless it misses by less than the re-evaluation threshold
+            const double q = fabs(xsub(in, fmin(fmax(in, 0.0), lim)));
+            danger |= gate & (q > 0.0) & (q < EDF_FAST_EPS);
+            return true;
+        }
+        danger |= gate & edf_near_half_integer(in);
+        cc = edf_map_coordinate_cold(in, p.idim[h], mode);
+        if (!(cc > -1.0)) return true;
+    }
+    const double fl = (ORDER & 1) ? floor(cc) : floor(xadd(cc, 0.5));
+    frac = (float)xsub(cc, fl);
+    start = (int)fl - ORDER / 2;
+    // float-side test, a superset of |2*in - rint(2*in)| < 2*EDF_FAST_EPS: odd orders have their
+    // thresholds at the integers, even orders at the half-integers (and the boundary tests at the
+    // integers 0 and len-1)
+    if (ORDER & 1) danger |= gate & ((frac < EDF_LEAN_EPSF) | (frac > 1.0f - EDF_LEAN_EPSF));
+    else           danger |= gate & ((fabsf(frac) < EDF_LEAN_EPSF) | (fabsf(frac) > 0.5f - EDF_LEAN_EPSF));
+    return false;
+}
+
+template <int ORDER, bool GRAD>
+__global__ void __launch_bounds__(EDF_FAST_THREADS, 2)
+edf_lean3d_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii)
+{
+    __shared__ EdfLeanSmem s;
+    constexpr int NT = ORDER + 1;
+    constexpr int NCHUNK = EDF_FAST_RY / EDF_FAST_M;
+    const int x0 = blockIdx.x * EDF_FAST_TX;
+    const int y0 = blockIdx.y * EDF_FAST_RY;
+    const int z0 = blockIdx.z * EDF_FAST_G;
+    edf_lean_tile_setup(p, s, z0, y0, x0);
+
+    const int tx = threadIdx.x & (EDF_FAST_TX - 1);
+    const int g = threadIdx.x >> 6;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = x0 + tx, z = z0 + g;
+    const int odz = (int)p.odim[0], ody = (int)p.odim[1], odx = (int)p.odim[2];
+    const bool tok = (x < odx) && (z < odz);
+    double wx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wx[k] = s.wx[tx][k];
+    const int sxrel = s.sx[tx] - s.sx[0];
+    const int nchunk = min(NCHUNK, (ody - y0 + EDF_FAST_M - 1) / EDF_FAST_M);
+    const bool gate = s.nonzero != 0;
+    const int nx = s.nx, sy_min = s.sy[0];
+    double (*Bw)[EDF_FAST_M][EDF_FAST_NC] = s.Bw[warp];
+
+    // per-thread constants of this input
+    const EdfInputDesc& d = p.inp[ii];
+    float* __restrict__ pin = (float*)d.in;                     // forward: read; gradient: accumulated
+    float* __restrict__ pout = (float*)d.out;                   // forward: written; gradient: dY
+    const int lenz = (int)p.idim[0], leny = (int)p.idim[1], lenx = (int)p.idim[2];
+    const double limz = p.idim_m1[0], limy = p.idim_m1[1], limx = p.idim_m1[2];
+    const int isz = L.istr_e[ii][0], isy = L.istr_e[ii][1];
+    const int osy = L.ostr_e[ii][1];
+    const int64_t obase_zx = (int64_t)z * L.ostr_e[ii][0] + (int64_t)x * L.ostr_e[ii][2];
+    const bool affine = p.has_affine != 0;
+    const int mode = d.mode;
+    const float cvalf = __uint_as_float((uint32_t)L.cval_bits[ii]);
+    const double bz = xadd((double)z, p.ooff_d[0]);             // deform.c:778-781: (o + offset) + displacement
+    const double bx = xadd((double)x, p.ooff_d[2]);
+    const double offy = p.ooff_d[1];
+
+    for (int c = 0; c < nchunk; ++c) {
+        // ---- y-contraction of this warp's slab for the 8 rows of the chunk (warp-private)
+        for (int e = lane; e < 3 * EDF_FAST_M * nx; e += 32) {
+            const int jx = e % nx;
+            const int m = (e / nx) % EDF_FAST_M;
+            const int h = e / (nx * EDF_FAST_M);
+            const int row = c * EDF_FAST_M + m;
+            const int r0 = s.sy[row] - sy_min;
+            double b = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b = fma(s.A[h][g][r0 + j][jx], s.wy[row][j], b);
+            Bw[h][m][jx] = b;
+        }
+        __syncwarp();
+        if (tok) {
+#pragma unroll 1
+            for (int m = 0; m < EDF_FAST_M; ++m) {
+                const int y = y0 + c * EDF_FAST_M + m;
+                if (y >= ody) break;
+                // ---- displacement: x-contraction of the tile tables (12 fp64 FMAs)
+                double dz = 0.0, dy = 0.0, dx = 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    dz = fma(Bw[0][m][sxrel + k], wx[k], dz);
+                    dy = fma(Bw[1][m][sxrel + k], wx[k], dy);
+                    dx = fma(Bw[2][m][sxrel + k], wx[k], dx);
+                }
+                double inz, iny, inx;
+                if (!affine) {
+                    inz = xadd(bz, dz);
+                    iny = xadd(xadd((double)y, offy), dy);
+                    inx = xadd(bx, dx);
+                } else {
+                    const int o[3] = {z, y, x};
+                    inz = edf_source_coordinate<3, int>(p, o, 0, dz);
+                    iny = edf_source_coordinate<3, int>(p, o, 1, dy);
+                    inx = edf_source_coordinate<3, int>(p, o, 2, dx);
+                }
+                // ---- boundary map, window start, fractional offsets; voxels next to a rounding /
+                //      boundary threshold are re-evaluated once in the exact reference order
+                int stz = 0, sty = 0, stx = 0;
+                float fz = 0.f, fy = 0.f, fx = 0.f;
+                bool constant, danger;
+#pragma unroll 1
+                for (int pass = 0;; ++pass) {
+                    danger = false;
+                    constant = edf_lean_axis<ORDER>(p, 0, mode, inz, limz, gate, stz, fz, danger);
+                    if (!constant) constant = edf_lean_axis<ORDER>(p, 1, mode, iny, limy, gate, sty, fy, danger);
+                    if (!constant) constant = edf_lean_axis<ORDER>(p, 2, mode, inx, limx, gate, stx, fx, danger);
+                    if (!danger || pass) break;
+                    edf_lean_exact_coords(p, z, y, x, &inz, &iny, &inx);
+                }
+                float* po = pout + (obase_zx + (int64_t)y * osy);
+                if (constant) {
+                    if (!GRAD) *po = cvalf;                                 // deform.c:903
+                    continue;
+                }
+                // ---- tap rows: element offsets along z and y with the reference's mirror mapping at
+                //      the edges (deform.c:791-813); the x taps are consecutive unless the x window
+                //      itself crosses the border somewhere in the warp
+                int oz[NT], oy[NT];
+                {
+                    const bool ez = (stz < 0) | (stz + ORDER >= lenz);
+                    const bool ey = (sty < 0) | (sty + ORDER >= leny);
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) {
+                        int iz = stz + i, iy = sty + i;
+                        if (ez) iz = edf_mirror_index32(iz, lenz);
+                        if (ey) iy = edf_mirror_index32(iy, leny);
+                        oz[i] = iz * isz;
+                        oy[i] = iy * isy;
+                    }
+                }
+                const bool ex = (stx < 0) | (stx + ORDER >= lenx);
+                float wz[NT], wy[NT], wxf[NT];
+                if (ORDER > 0) {
+                    edf_bspline_weights_f32<ORDER>(fz, wz);
+                    edf_bspline_weights_f32<ORDER>(fy, wy);
+                    edf_bspline_weights_f32<ORDER>(fx, wxf);
+                }
+                const bool warp_ex = __any_sync(__activemask(), ex);
+                if (!GRAD) {
+                    float t = 0.f;
+                    if (!warp_ex) {
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) {
+                            float ti = 0.f;
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) {
+                                const float* r = pin + (oz[i] + oy[j] + stx);
+                                float tj = (ORDER > 0) ? __ldg(r) * wxf[0] : __ldg(r);
+#pragma unroll
+                                for (int k = 1; k < NT; ++k) tj = fmaf(__ldg(r + k), wxf[k], tj);
+                                if (ORDER > 0) ti = (j == 0) ? tj * wy[0] : fmaf(tj, wy[j], ti);
+                                else ti = tj;
+                            }
+                            if (ORDER > 0) t = (i == 0) ? ti * wz[0] : fmaf(ti, wz[i], t);
+                            else t = ti;
+                        }
+                    } else {
+                        int oxk[NT];
+#pragma unroll
+                        for (int k = 0; k < NT; ++k) oxk[k] = ex ? edf_mirror_index32(stx + k, lenx) : stx + k;
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) {
+                            float ti = 0.f;
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) {
+                                const float* r = pin + (oz[i] + oy[j]);
+                                float tj = (ORDER > 0) ? __ldg(r + oxk[0]) * wxf[0] : __ldg(r + oxk[0]);
+#pragma unroll
+                                for (int k = 1; k < NT; ++k) tj = fmaf(__ldg(r + oxk[k]), wxf[k], tj);
+                                if (ORDER > 0) ti = (j == 0) ? tj * wy[0] : fmaf(tj, wy[j], ti);
+                                else ti = tj;
+                            }
+                            if (ORDER > 0) t = (i == 0) ? ti * wz[0] : fmaf(ti, wz[i], t);
+                            else t = ti;
+                        }
+                    }
+                    *po = t;
+                } else {
+                    const float gval = *po;
+                    int oxk[NT];
+#pragma unroll
+                    for (int k = 0; k < NT; ++k) oxk[k] = ex ? edf_mirror_index32(stx + k, lenx) : stx + k;
+#pragma unroll
+                    for (int i = 0; i < NT; ++i) {
+                        const float gi = (ORDER > 0) ? gval * wz[i] : gval;
+#pragma unroll
+                        for (int j = 0; j < NT; ++j) {
+                            const float gj = (ORDER > 0) ? gi * wy[j] : gi;
+                            float* r = pin + (oz[i] + oy[j]);
+#pragma unroll
+                            for (int k = 0; k < NT; ++k)
+                                atomicAdd(r + oxk[k], (ORDER > 0) ? gj * wxf[k] : gj);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static bool edf_lean_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii)
+{
+    if (p.naxis != 3) return false;
+    const EdfInputDesc& d = p.inp[ii];
+    if (d.in_dtype != EDF_F32 || d.out_dtype != EDF_F32) return false;
+    if (d.nstep_rank != 0) return false;
+    if (L.istr_e[ii][2] != 1) return false;
+    return true;
+}
+
+static void edf_lean_launch(int order, int gradient, dim3 grid, cudaStream_t st, const EdfParams& p,
+                            const EdfFastLaunch& L, int ii)
+{
+#define EDF_LEAN_CASE(O)                                                                       \
+    case O:                                                                                    \
+        if (gradient) edf_lean3d_kernel<O, true><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii);  \
+        else          edf_lean3d_kernel<O, false><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); \
+        break;
+    switch (order) {
+        EDF_LEAN_CASE(0) EDF_LEAN_CASE(1) EDF_LEAN_CASE(2) EDF_LEAN_CASE(3) EDF_LEAN_CASE(4)
+    default:
+        if (gradient) edf_lean3d_kernel<5, true><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii);
+        else          edf_lean3d_kernel<5, false><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii);
+        break;
+    }
+#undef EDF_LEAN_CASE
+}
