@@ -540,6 +540,8 @@ static void edf_fast_launch_copy(int es, dim3 grid, cudaStream_t st, const EdfPa
 static bool edf_lean_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii);
 static void edf_lean_launch(int order, int gradient, dim3 grid, cudaStream_t st, const EdfParams& p,
                             const EdfFastLaunch& L, int ii);
+static int edf_lean_launch_gradwin(int order, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii);
+static bool edf_gradwin_eligible(const EdfParams& p);
 
 // Tries to run (part of) the problem on the specialised kernels.
 //   *handled_mask receives the inputs that were processed (the caller runs the generic
@@ -575,10 +577,15 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
         if (done[ii] || cls[ii] == EDF_CLASS_NONE) continue;
         if (cls[ii] == EDF_CLASS_F32 && edf_lean_eligible(p, L, ii)) {
             L.input_mask = 1u << ii;
-            edf_lean_launch(p.inp[ii].order, p.gradient, grid, st, p, L, ii);
+            if (p.gradient && edf_gradwin_eligible(p)) {
+                if (edf_lean_launch_gradwin(p.inp[ii].order, st, p, L, ii) < 0) return -1;
+                *name = "lean3d_f32_gradwin";
+            } else {
+                edf_lean_launch(p.inp[ii].order, p.gradient, grid, st, p, L, ii);
+                *name = p.gradient ? "lean3d_f32_grad" : "lean3d_f32";
+            }
             g_fast_launch_error = cudaGetLastError();
             if (g_fast_launch_error != cudaSuccess) return -1;
-            *name = p.gradient ? "lean3d_f32_grad" : "lean3d_f32";
             done[ii] = true;
             ++launches;
             *handled_mask |= 1u << ii;

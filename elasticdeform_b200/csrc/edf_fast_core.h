@@ -45,14 +45,14 @@ EDF_HD void edf_fast_ctrl_entry(const EdfParams& p, int a, int64_t o, double* w4
 
 // Can the fast path's fixed-size tables hold the control points a tile touches?
 // (span of window starts over T consecutive outputs, plus the 4-tap window)
-EDF_HD bool edf_fast_ctrl_span_ok(const EdfParams& p, int a, int T)
+EDF_HD bool edf_fast_ctrl_span_ok(const EdfParams& p, int a, int T, int NC = EDF_FAST_NC)
 {
     if (p.idim[a] < 2) return false;                        // cp = x/0 in the reference
     // starts differ by at most ceil((T-1)*(P-1)/(I-1)) over a tile
     const int64_t num = (int64_t)(T - 1) * (p.ncp[a] - 1);
     const int64_t den = p.idim[a] - 1;
     const int64_t span = (num + den - 1) / den + 1;
-    return span + 4 <= EDF_FAST_NC;
+    return span + 4 <= NC;
 }
 
 // Finish one axis for one input: boundary map, window start, fractional offset.

@@ -329,3 +329,349 @@ static void edf_lean_launch(int order, int gradient, dim3 grid, cudaStream_t st,
     }
 #undef EDF_LEAN_CASE
 }
+
+// =======================================================================================
+// Gradient scatter with a shared-memory accumulation window (K2).
+//
+// The plain scatter issues (order+1)^3 global float atomics per voxel whose addresses coalesce
+// badly (~10 L2 atomic requests per warp instruction): it is bound by L2 atomic throughput.
+// Here a CTA (4 warps = 4 z-slabs x 32 x positions) accumulates the contributions of a chunk of
+// 8 rows into a window of the dX volume held in shared memory and then adds the window to dX
+// with perfectly coalesced atomics (each touched cell once per chunk, ~10 per voxel instead of
+// 64).  Shared-memory float atomics are CAS loops on sm_100 (ATOMS.CAST.SPIN), so the window
+// accumulates in 32-bit FIXED POINT with native ATOMS.ADD: contributions are scaled so that
+// the chunk's max |dY| maps to 2^22 (absolute resolution max|dY_chunk| * 2^-23, headroom 512x);
+// the flush converts back and adds in float.  Voxels whose tap window touches the volume border
+// or does not fit the accumulation window fall back to direct global atomics.
+// =======================================================================================
+#define EDF_GW_TX 32               // x positions per warp / CTA
+#define EDF_GW_G 8                 // z-slabs (= warps) per CTA
+#define EDF_GW_THREADS (EDF_GW_TX * EDF_GW_G)
+#define EDF_GW_NC 8                // control-point span capacity of this kernel's tables
+#define EDF_GW_WZ 22               // accumulation window (cells of dX) around the chunk's footprint
+#define EDF_GW_WY 20
+#define EDF_GW_WX 44               // multiple of 4: the flush moves 16-byte groups
+#define EDF_GW_MARGIN 2
+#define EDF_GW_FIX 24              // chunk max |dY| maps into [2^(FIX-1), 2^FIX]
+
+struct EdfGradWinSmem {
+    double wz[EDF_GW_G][4];
+    double wy[EDF_FAST_RY][4];
+    double wx[EDF_GW_TX][4];
+    int    sz[EDF_GW_G];
+    int    sy[EDF_FAST_RY];
+    int    sx[EDF_GW_TX];
+    int    ny, nx, nonzero, gmax_bits;
+    int    wmin[3], pad_;
+    double A[3][EDF_GW_G][EDF_GW_NC][EDF_GW_NC];
+    double Bw[EDF_GW_G][3][EDF_FAST_M][EDF_GW_NC];
+    __align__(16) int win[EDF_GW_WZ * EDF_GW_WY * EDF_GW_WX];
+};
+
+// un-mapped source coordinates of voxel (z, y, x) from the warp's B table (same arithmetic as the
+// forward lean kernel)
+__device__ __forceinline__ void edf_gw_coords(const EdfParams& p, const double (*Bw)[EDF_FAST_M][EDF_GW_NC],
+                                              int m, int sxrel, const double* wx, bool affine, int z, int y, int x,
+                                              double bz, double bx, double offy, double& inz, double& iny, double& inx)
+{
+    double dz = 0.0, dy = 0.0, dx = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        dz = fma(Bw[0][m][sxrel + k], wx[k], dz);
+        dy = fma(Bw[1][m][sxrel + k], wx[k], dy);
+        dx = fma(Bw[2][m][sxrel + k], wx[k], dx);
+    }
+    if (!affine) {
+        inz = xadd(bz, dz);
+        iny = xadd(xadd((double)y, offy), dy);
+        inx = xadd(bx, dx);
+    } else {
+        const int o[3] = {z, y, x};
+        inz = edf_source_coordinate<3, int>(p, o, 0, dz);
+        iny = edf_source_coordinate<3, int>(p, o, 1, dy);
+        inx = edf_source_coordinate<3, int>(p, o, 2, dx);
+    }
+}
+
+template <int ORDER, bool VEC>
+__global__ void __launch_bounds__(EDF_GW_THREADS, 2)
+edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EdfGradWinSmem& s = *reinterpret_cast<EdfGradWinSmem*>(smem_raw);
+    constexpr int NT = ORDER + 1;
+    constexpr int NCHUNK = EDF_FAST_RY / EDF_FAST_M;
+    constexpr int NWIN = EDF_GW_WZ * EDF_GW_WY * EDF_GW_WX;
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * EDF_GW_TX;
+    const int y0 = blockIdx.y * EDF_FAST_RY;
+    const int z0 = blockIdx.z * EDF_GW_G;
+
+    // ---- prologue: control tables, z-contraction A, zeroed window
+    if (tid == 0) s.nonzero = 0;
+    if (tid < EDF_GW_TX) {
+        edf_fast_ctrl_entry(p, 2, min((int64_t)(x0 + tid), p.odim[2] - 1), s.wx[tid], &s.sx[tid]);
+    } else if (tid < EDF_GW_TX + EDF_FAST_RY) {
+        const int t = tid - EDF_GW_TX;
+        edf_fast_ctrl_entry(p, 1, min((int64_t)(y0 + t), p.odim[1] - 1), s.wy[t], &s.sy[t]);
+    } else if (tid < EDF_GW_TX + EDF_FAST_RY + EDF_GW_G) {
+        const int t = tid - EDF_GW_TX - EDF_FAST_RY;
+        edf_fast_ctrl_entry(p, 0, min((int64_t)(z0 + t), p.odim[0] - 1), s.wz[t], &s.sz[t]);
+    }
+    for (int e = tid; e < NWIN; e += EDF_GW_THREADS) s.win[e] = 0;
+    __syncthreads();
+    {
+        const int sy_min0 = s.sy[0], sx_min0 = s.sx[0];
+        const int ny = s.sy[EDF_FAST_RY - 1] - sy_min0 + 4;
+        const int nxx = s.sx[EDF_GW_TX - 1] - sx_min0 + 4;
+        if (tid == 0) { s.ny = ny; s.nx = nxx; }
+        bool nz = false;
+        const int na = 3 * EDF_GW_G * ny * nxx;
+        for (int e = tid; e < na; e += EDF_GW_THREADS) {
+            const int jx = e % nxx;
+            const int jy = (e / nxx) % ny;
+            const int t = (e / (nxx * ny)) % EDF_GW_G;
+            const int h = e / (nxx * ny * EDF_GW_G);
+            const int my = edf_mirror_index32(sy_min0 + jy, (int)p.ncp[1]);
+            const int mx = edf_mirror_index32(sx_min0 + jx, (int)p.ncp[2]);
+            const char* base = p.disp + p.dstr[0] * h + my * p.dstr[2] + mx * p.dstr[3];
+            double a = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int mz = edf_mirror_index32(s.sz[t] + i, (int)p.ncp[0]);
+                const double cf = (p.ddtype == EDF_F64) ? *(const double*)(base + mz * p.dstr[1])
+                                                        : (double)*(const float*)(base + mz * p.dstr[1]);
+                nz |= (cf != 0.0);
+                a = fma(cf, s.wz[t][i], a);
+            }
+            s.A[h][t][jy][jx] = a;
+        }
+        if (nz) s.nonzero = 1;
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, g = tid >> 5;                    // one warp per z-slab
+    const int x = x0 + lane, z = z0 + g;
+    const int odz = (int)p.odim[0], ody = (int)p.odim[1], odx = (int)p.odim[2];
+    const bool tok = (x < odx) && (z < odz);
+    double wx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wx[k] = s.wx[lane][k];
+    const int sxrel = s.sx[lane] - s.sx[0];
+    const int nchunk = min(NCHUNK, (ody - y0 + EDF_FAST_M - 1) / EDF_FAST_M);
+    const bool gate = s.nonzero != 0;
+    const int nx = s.nx, sy_min = s.sy[0];
+    double (*Bw)[EDF_FAST_M][EDF_GW_NC] = s.Bw[g];
+
+    const EdfInputDesc& d = p.inp[ii];
+    float* __restrict__ pdx = (float*)d.in;                      // dX accumulator
+    const float* __restrict__ pdy = (const float*)d.out;         // upstream gradient dY
+    const int lenz = (int)p.idim[0], leny = (int)p.idim[1], lenx = (int)p.idim[2];
+    const double limz = p.idim_m1[0], limy = p.idim_m1[1], limx = p.idim_m1[2];
+    const int isz = L.istr_e[ii][0], isy = L.istr_e[ii][1];
+    const int osy = L.ostr_e[ii][1];
+    const int64_t obase_zx = (int64_t)z * L.ostr_e[ii][0] + (int64_t)x * L.ostr_e[ii][2];
+    const bool affine = p.has_affine != 0;
+    const int mode = d.mode;
+    const double bz = xadd((double)z, p.ooff_d[0]);
+    const double bx = xadd((double)x, p.ooff_d[2]);
+    const double offy = p.ooff_d[1];
+    const int ozmax = odz - 1 - z0 < EDF_GW_G - 1 ? odz - 1 - z0 : EDF_GW_G - 1;   // last valid slab
+    const int oxmax = odx - 1 - x0 < EDF_GW_TX - 1 ? odx - 1 - x0 : EDF_GW_TX - 1;     // last valid lane
+
+    for (int c = 0; c < nchunk; ++c) {
+        const int yc0 = y0 + c * EDF_FAST_M;
+        const int mlast = min(EDF_FAST_M - 1, ody - 1 - yc0);
+        // ---- warp-private y-contraction for the 8 rows of the chunk
+        for (int e = lane; e < 3 * EDF_FAST_M * nx; e += 32) {
+            const int jx = e % nx;
+            const int m = (e / nx) % EDF_FAST_M;
+            const int h = e / (nx * EDF_FAST_M);
+            const int row = c * EDF_FAST_M + m;
+            const int r0 = s.sy[row] - sy_min;
+            double b = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b = fma(s.A[h][g][r0 + j][jx], s.wy[row][j], b);
+            Bw[h][m][jx] = b;
+        }
+        if (tid == 0) { s.wmin[0] = s.wmin[1] = s.wmin[2] = 0x7fffffff; s.gmax_bits = 0; }
+        __syncthreads();
+        // ---- chunk statistics: max |dY| (fixed-point scale) and the window origin from the
+        //      corner voxels of the chunk box
+        float gmax = 0.f;
+#pragma unroll
+        for (int m = 0; m < EDF_FAST_M; ++m) {
+            const float gq = (tok && m <= mlast) ? __ldg(pdy + (obase_zx + (int64_t)(yc0 + m) * osy)) : 0.f;
+            gmax = fmaxf(gmax, fabsf(gq));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        if (lane == 0 && gmax > 0.f) atomicMax(&s.gmax_bits, __float_as_int(gmax));
+        if ((g == 0 || g == ozmax) && (lane == 0 || lane == oxmax) && tok) {
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q) {
+                const int m = q ? mlast : 0;
+                double inz, iny, inx;
+                edf_gw_coords(p, Bw, m, sxrel, wx, affine, z, yc0 + m, x, bz, bx, offy, inz, iny, inx);
+                // floor of the clamped coordinate: out-of-volume corners must not drag the window away
+                const int fz_ = (int)floor(fmin(fmax(inz, 0.0), limz));
+                const int fy_ = (int)floor(fmin(fmax(iny, 0.0), limy));
+                const int fx_ = (int)floor(fmin(fmax(inx, 0.0), limx));
+                atomicMin(&s.wmin[0], fz_);
+                atomicMin(&s.wmin[1], fy_);
+                atomicMin(&s.wmin[2], fx_);
+            }
+        }
+        __syncthreads();
+        const float gmax_c = __int_as_float(s.gmax_bits);
+        if (gmax_c > 0.f) {                                       // an all-zero chunk contributes nothing
+            // power-of-two scale: max|dY| of the chunk -> [2^(FIX-1), 2^FIX]
+            int ex;
+            frexpf(gmax_c, &ex);                                  // gmax = f * 2^ex, f in [0.5, 1)
+            const float scale = ldexpf(1.0f, EDF_GW_FIX - ex);
+            const float inv_scale = ldexpf(1.0f, ex - EDF_GW_FIX);
+            const int wz0 = s.wmin[0] - (ORDER + 1) / 2 - EDF_GW_MARGIN;
+            const int wy0 = s.wmin[1] - (ORDER + 1) / 2 - EDF_GW_MARGIN;
+            const int wx0 = (s.wmin[2] - (ORDER + 1) / 2 - EDF_GW_MARGIN) & ~3;   // 16-byte aligned columns
+            if (tok) {
+#pragma unroll 1
+                for (int m = 0; m <= mlast; ++m) {
+                    const int y = yc0 + m;
+                    const float gval = __ldg(pdy + (obase_zx + (int64_t)y * osy));   // L1 hit (read above)
+                    if (gval == 0.f) continue;
+                    double inz, iny, inx;
+                    edf_gw_coords(p, Bw, m, sxrel, wx, affine, z, y, x, bz, bx, offy, inz, iny, inx);
+                    int stz = 0, sty = 0, stx = 0;
+                    float fz = 0.f, fy = 0.f, fx = 0.f;
+                    bool constant, danger;
+#pragma unroll 1
+                    for (int pass = 0;; ++pass) {
+                        danger = false;
+                        constant = edf_lean_axis<ORDER>(p, 0, mode, inz, limz, gate, stz, fz, danger);
+                        if (!constant) constant = edf_lean_axis<ORDER>(p, 1, mode, iny, limy, gate, sty, fy, danger);
+                        if (!constant) constant = edf_lean_axis<ORDER>(p, 2, mode, inx, limx, gate, stx, fx, danger);
+                        if (!danger || pass) break;
+                        edf_lean_exact_coords(p, z, y, x, &inz, &iny, &inx);
+                    }
+                    if (constant) continue;                        // deform.c:928: no gradient through cval
+                    float wzf[NT], wyf[NT], wxf[NT];
+                    if (ORDER > 0) {
+                        edf_bspline_weights_f32<ORDER>(fz, wzf);
+                        edf_bspline_weights_f32<ORDER>(fy, wyf);
+                        edf_bspline_weights_f32<ORDER>(fx, wxf);
+                    }
+                    const bool edge = (stz < 0) | (stz + ORDER >= lenz) | (sty < 0) | (sty + ORDER >= leny) |
+                                      (stx < 0) | (stx + ORDER >= lenx);
+                    const int rz = stz - wz0, ry = sty - wy0, rx = stx - wx0;
+                    const bool inwin = (rz >= 0) & (rz + ORDER < EDF_GW_WZ) & (ry >= 0) & (ry + ORDER < EDF_GW_WY) &
+                                       (rx >= 0) & (rx + ORDER < EDF_GW_WX);
+                    if (!edge && inwin) {
+                        int* wbase = s.win + ((rz * EDF_GW_WY + ry) * EDF_GW_WX + rx);
+                        const float gs = gval * scale;
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) {
+                            const float gi = (ORDER > 0) ? gs * wzf[i] : gs;
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) {
+                                const float gj = (ORDER > 0) ? gi * wyf[j] : gi;
+                                int* r = wbase + (i * EDF_GW_WY + j) * EDF_GW_WX;
+#pragma unroll
+                                for (int k = 0; k < NT; ++k)
+                                    atomicAdd(r + k, __float2int_rn((ORDER > 0) ? gj * wxf[k] : gj));
+                            }
+                        }
+                    } else {
+                        // border of the volume / outside the accumulation window: direct global atomics
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) {
+                            const float gi = (ORDER > 0) ? gval * wzf[i] : gval;
+                            const int iz = edf_mirror_index32(stz + i, lenz) * isz;
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) {
+                                const float gj = (ORDER > 0) ? gi * wyf[j] : gi;
+                                float* r = pdx + (iz + edf_mirror_index32(sty + j, leny) * isy);
+#pragma unroll
+                                for (int k = 0; k < NT; ++k)
+                                    atomicAdd(r + edf_mirror_index32(stx + k, lenx), (ORDER > 0) ? gj * wxf[k] : gj);
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- flush: every touched window cell once, coalesced along x, and re-zero
+            if (VEC) {
+                for (int q = tid; q < NWIN / 4; q += EDF_GW_THREADS) {
+                    int4 v = reinterpret_cast<int4*>(s.win)[q];
+                    if ((v.x | v.y | v.z | v.w) != 0) {
+                        reinterpret_cast<int4*>(s.win)[q] = make_int4(0, 0, 0, 0);
+                        const int ix = (q % (EDF_GW_WX / 4)) * 4;
+                        const int iy = (q / (EDF_GW_WX / 4)) % EDF_GW_WY;
+                        const int iz = q / ((EDF_GW_WX / 4) * EDF_GW_WY);
+                        float4* dst = reinterpret_cast<float4*>(pdx + ((wz0 + iz) * isz + (wy0 + iy) * isy + (wx0 + ix)));
+                        atomicAdd(dst, make_float4((float)v.x * inv_scale, (float)v.y * inv_scale,
+                                                   (float)v.z * inv_scale, (float)v.w * inv_scale));
+                    }
+                }
+            } else {
+                for (int e = tid; e < NWIN; e += EDF_GW_THREADS) {
+                    const int v = s.win[e];
+                    if (v != 0) {
+                        s.win[e] = 0;
+                        const int ix = e % EDF_GW_WX;
+                        const int iy = (e / EDF_GW_WX) % EDF_GW_WY;
+                        const int iz = e / (EDF_GW_WX * EDF_GW_WY);
+                        atomicAdd(pdx + ((wz0 + iz) * isz + (wy0 + iy) * isy + (wx0 + ix)), (float)v * inv_scale);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static bool g_gradwin_configured = false;
+
+// The window kernel uses 32-lane x tiles; its control-point tables must hold a 32-wide span, and
+// dX element offsets must fit 32 bits (already guaranteed by edf_fast_input_class).
+static bool edf_gradwin_eligible(const EdfParams& p)
+{
+    static int disabled = -1;
+    if (disabled < 0) { const char* e = getenv("EDF_NO_GRADWIN"); disabled = (e && *e && *e != '0') ? 1 : 0; }
+    if (disabled) return false;
+    return p.naxis == 3 && edf_fast_ctrl_span_ok(p, 2, EDF_GW_TX, EDF_GW_NC) && edf_fast_ctrl_span_ok(p, 1, EDF_FAST_RY, EDF_GW_NC);
+}
+
+static int edf_lean_launch_gradwin(int order, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii)
+{
+    dim3 grid;
+    grid.x = (unsigned)((p.odim[2] + EDF_GW_TX - 1) / EDF_GW_TX);
+    grid.y = (unsigned)((p.odim[1] + EDF_FAST_RY - 1) / EDF_FAST_RY);
+    grid.z = (unsigned)((p.odim[0] + EDF_GW_G - 1) / EDF_GW_G);
+    const size_t smem = sizeof(EdfGradWinSmem);
+    if (!g_gradwin_configured) {
+#define EDF_GW_ATTR(O)                                                                                              \
+    cudaFuncSetAttribute(edf_lean3d_gradwin_kernel<O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaFuncSetAttribute(edf_lean3d_gradwin_kernel<O, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        EDF_GW_ATTR(0); EDF_GW_ATTR(1); EDF_GW_ATTR(2); EDF_GW_ATTR(3); EDF_GW_ATTR(4); EDF_GW_ATTR(5);
+#undef EDF_GW_ATTR
+        if (cudaGetLastError() != cudaSuccess) return -1;
+        g_gradwin_configured = true;
+    }
+    // 16-byte vector flush needs 16-byte aligned rows of dX
+    const bool vec = ((uintptr_t)p.inp[ii].in % 16 == 0) && (L.istr_e[ii][0] % 4 == 0) && (L.istr_e[ii][1] % 4 == 0);
+#define EDF_GW_CASE(O)                                                                                     \
+    case O:                                                                                                \
+        if (vec) edf_lean3d_gradwin_kernel<O, true><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii);          \
+        else     edf_lean3d_gradwin_kernel<O, false><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii);         \
+        break;
+    switch (order) {
+        EDF_GW_CASE(0) EDF_GW_CASE(1) EDF_GW_CASE(2) EDF_GW_CASE(3) EDF_GW_CASE(4)
+    default:
+        if (vec) edf_lean3d_gradwin_kernel<5, true><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii);
+        else     edf_lean3d_gradwin_kernel<5, false><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii);
+        break;
+    }
+#undef EDF_GW_CASE
+    return 0;
+}
