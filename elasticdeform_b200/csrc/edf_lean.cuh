@@ -345,12 +345,15 @@ static void edf_lean_launch(int order, int gradient, dim3 grid, cudaStream_t st,
 // or does not fit the accumulation window fall back to direct global atomics.
 // =======================================================================================
 #define EDF_GW_TX 32               // x positions per warp / CTA
-#define EDF_GW_G 8                 // z-slabs (= warps) per CTA
-#define EDF_GW_THREADS (EDF_GW_TX * EDF_GW_G)
+#define EDF_GW_G 4                 // z-slabs per CTA
+#define EDF_GW_RG 2                // row groups: warp w owns slab (w % G) and rows rg*MR .. rg*MR+MR-1 of a chunk
+#define EDF_GW_MR (EDF_FAST_M / EDF_GW_RG)
+#define EDF_GW_WARPS (EDF_GW_G * EDF_GW_RG)
+#define EDF_GW_THREADS (EDF_GW_TX * EDF_GW_WARPS)
 #define EDF_GW_NC 8                // control-point span capacity of this kernel's tables
-#define EDF_GW_WZ 22               // accumulation window (cells of dX) around the chunk's footprint
-#define EDF_GW_WY 20
-#define EDF_GW_WX 44               // multiple of 4: the flush moves 16-byte groups
+#define EDF_GW_WZ 19               // accumulation window (cells of dX) around the chunk's footprint:
+#define EDF_GW_WY 23               //   tile extent + taps + ~0.2 x (other extents) + margins
+#define EDF_GW_WX 52               // multiple of 4: the flush moves 16-byte groups
 #define EDF_GW_MARGIN 2
 #define EDF_GW_FIX 24              // chunk max |dY| maps into [2^(FIX-1), 2^FIX]
 
@@ -364,13 +367,13 @@ struct EdfGradWinSmem {
     int    ny, nx, nonzero, gmax_bits;
     int    wmin[3], pad_;
     double A[3][EDF_GW_G][EDF_GW_NC][EDF_GW_NC];
-    double Bw[EDF_GW_G][3][EDF_FAST_M][EDF_GW_NC];
+    double Bw[EDF_GW_WARPS][3][EDF_GW_MR][EDF_GW_NC];
     __align__(16) int win[EDF_GW_WZ * EDF_GW_WY * EDF_GW_WX];
 };
 
 // un-mapped source coordinates of voxel (z, y, x) from the warp's B table (same arithmetic as the
 // forward lean kernel)
-__device__ __forceinline__ void edf_gw_coords(const EdfParams& p, const double (*Bw)[EDF_FAST_M][EDF_GW_NC],
+__device__ __forceinline__ void edf_gw_coords(const EdfParams& p, const double (*Bw)[EDF_GW_MR][EDF_GW_NC],
                                               int m, int sxrel, const double* wx, bool affine, int z, int y, int x,
                                               double bz, double bx, double offy, double& inz, double& iny, double& inx)
 {
@@ -450,7 +453,8 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
     }
     __syncthreads();
 
-    const int lane = tid & 31, g = tid >> 5;                    // one warp per z-slab
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = warp % EDF_GW_G, rg = warp / EDF_GW_G;          // slab and row group of this warp
     const int x = x0 + lane, z = z0 + g;
     const int odz = (int)p.odim[0], ody = (int)p.odim[1], odx = (int)p.odim[2];
     const bool tok = (x < odx) && (z < odz);
@@ -461,7 +465,7 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
     const int nchunk = min(NCHUNK, (ody - y0 + EDF_FAST_M - 1) / EDF_FAST_M);
     const bool gate = s.nonzero != 0;
     const int nx = s.nx, sy_min = s.sy[0];
-    double (*Bw)[EDF_FAST_M][EDF_GW_NC] = s.Bw[g];
+    double (*Bw)[EDF_GW_MR][EDF_GW_NC] = s.Bw[warp];
 
     const EdfInputDesc& d = p.inp[ii];
     float* __restrict__ pdx = (float*)d.in;                      // dX accumulator
@@ -482,12 +486,12 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
     for (int c = 0; c < nchunk; ++c) {
         const int yc0 = y0 + c * EDF_FAST_M;
         const int mlast = min(EDF_FAST_M - 1, ody - 1 - yc0);
-        // ---- warp-private y-contraction for the 8 rows of the chunk
-        for (int e = lane; e < 3 * EDF_FAST_M * nx; e += 32) {
+        // ---- warp-private y-contraction for this warp's rows of the chunk
+        for (int e = lane; e < 3 * EDF_GW_MR * nx; e += 32) {
             const int jx = e % nx;
-            const int m = (e / nx) % EDF_FAST_M;
-            const int h = e / (nx * EDF_FAST_M);
-            const int row = c * EDF_FAST_M + m;
+            const int m = (e / nx) % EDF_GW_MR;
+            const int h = e / (nx * EDF_GW_MR);
+            const int row = c * EDF_FAST_M + rg * EDF_GW_MR + m;
             const int r0 = s.sy[row] - sy_min;
             double b = 0.0;
 #pragma unroll
@@ -498,21 +502,23 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
         __syncthreads();
         // ---- chunk statistics: max |dY| (fixed-point scale) and the window origin from the
         //      corner voxels of the chunk box
+        const int mr0 = rg * EDF_GW_MR;                            // first row of this warp in the chunk
+        const int mrlast = min(EDF_GW_MR - 1, mlast - mr0);         // last valid local row (may be < 0)
         float gmax = 0.f;
 #pragma unroll
-        for (int m = 0; m < EDF_FAST_M; ++m) {
-            const float gq = (tok && m <= mlast) ? __ldg(pdy + (obase_zx + (int64_t)(yc0 + m) * osy)) : 0.f;
+        for (int m = 0; m < EDF_GW_MR; ++m) {
+            const float gq = (tok && m <= mrlast) ? __ldg(pdy + (obase_zx + (int64_t)(yc0 + mr0 + m) * osy)) : 0.f;
             gmax = fmaxf(gmax, fabsf(gq));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
         if (lane == 0 && gmax > 0.f) atomicMax(&s.gmax_bits, __float_as_int(gmax));
-        if ((g == 0 || g == ozmax) && (lane == 0 || lane == oxmax) && tok) {
+        if ((g == 0 || g == ozmax) && (lane == 0 || lane == oxmax) && tok && mrlast >= 0) {
 #pragma unroll 1
             for (int q = 0; q < 2; ++q) {
-                const int m = q ? mlast : 0;
+                const int m = q ? mrlast : 0;
                 double inz, iny, inx;
-                edf_gw_coords(p, Bw, m, sxrel, wx, affine, z, yc0 + m, x, bz, bx, offy, inz, iny, inx);
+                edf_gw_coords(p, Bw, m, sxrel, wx, affine, z, yc0 + mr0 + m, x, bz, bx, offy, inz, iny, inx);
                 // floor of the clamped coordinate: out-of-volume corners must not drag the window away
                 const int fz_ = (int)floor(fmin(fmax(inz, 0.0), limz));
                 const int fy_ = (int)floor(fmin(fmax(iny, 0.0), limy));
@@ -535,8 +541,8 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
             const int wx0 = (s.wmin[2] - (ORDER + 1) / 2 - EDF_GW_MARGIN) & ~3;   // 16-byte aligned columns
             if (tok) {
 #pragma unroll 1
-                for (int m = 0; m <= mlast; ++m) {
-                    const int y = yc0 + m;
+                for (int m = 0; m <= mrlast; ++m) {
+                    const int y = yc0 + mr0 + m;
                     const float gval = __ldg(pdy + (obase_zx + (int64_t)y * osy));   // L1 hit (read above)
                     if (gval == 0.f) continue;
                     double inz, iny, inx;
@@ -582,17 +588,23 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
                         }
                     } else {
                         // border of the volume / outside the accumulation window: direct global atomics
+                        int ozt[NT], oyt[NT], oxt[NT];
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) {
+                            ozt[i] = edf_mirror_index32(stz + i, lenz) * isz;
+                            oyt[i] = edf_mirror_index32(sty + i, leny) * isy;
+                            oxt[i] = edf_mirror_index32(stx + i, lenx);
+                        }
 #pragma unroll
                         for (int i = 0; i < NT; ++i) {
                             const float gi = (ORDER > 0) ? gval * wzf[i] : gval;
-                            const int iz = edf_mirror_index32(stz + i, lenz) * isz;
 #pragma unroll
                             for (int j = 0; j < NT; ++j) {
                                 const float gj = (ORDER > 0) ? gi * wyf[j] : gi;
-                                float* r = pdx + (iz + edf_mirror_index32(sty + j, leny) * isy);
+                                float* r = pdx + (ozt[i] + oyt[j]);
 #pragma unroll
                                 for (int k = 0; k < NT; ++k)
-                                    atomicAdd(r + edf_mirror_index32(stx + k, lenx), (ORDER > 0) ? gj * wxf[k] : gj);
+                                    atomicAdd(r + oxt[k], (ORDER > 0) ? gj * wxf[k] : gj);
                             }
                         }
                     }
