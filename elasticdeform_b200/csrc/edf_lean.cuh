@@ -115,8 +115,8 @@ __device__ __forceinline__ bool edf_lean_axis(const EdfParams& p, int h, int mod
     return false;
 }
 
-template <int ORDER, bool GRAD>
-__global__ void __launch_bounds__(EDF_FAST_THREADS, 2)
+template <int ORDER, bool GRAD, int MINB = 2>
+__global__ void __launch_bounds__(EDF_FAST_THREADS, MINB)
 edf_lean3d_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii)
 {
     __shared__ EdfLeanSmem s;
@@ -315,6 +315,10 @@ static bool edf_lean_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii
 static void edf_lean_launch(int order, int gradient, dim3 grid, cudaStream_t st, const EdfParams& p,
                             const EdfFastLaunch& L, int ii)
 {
+    static int variant = -1;                  // experiment knob: occupancy target of the order-3 forward kernel
+    if (variant < 0) { const char* e = getenv("EDF_LEAN_VARIANT"); variant = e ? atoi(e) : 0; }
+    if (order == 3 && !gradient && variant == 1) { edf_lean3d_kernel<3, false, 3><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); return; }
+    if (order == 3 && !gradient && variant == 2) { edf_lean3d_kernel<3, false, 4><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); return; }
 #define EDF_LEAN_CASE(O)                                                                       \
     case O:                                                                                    \
         if (gradient) edf_lean3d_kernel<O, true><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii);  \
