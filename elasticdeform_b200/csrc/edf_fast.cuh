@@ -578,8 +578,9 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
         if (cls[ii] == EDF_CLASS_F32 && edf_lean_eligible(p, L, ii)) {
             L.input_mask = 1u << ii;
             if (p.gradient && edf_gradwin_eligible(p)) {
-                if (edf_lean_launch_gradwin(p.inp[ii].order, st, p, L, ii) < 0) return -1;
-                *name = "lean3d_f32_gradwin";
+                const int rcw = edf_lean_launch_gradwin(p.inp[ii].order, st, p, L, ii);
+                if (rcw < 0) return -1;
+                *name = rcw == 2 ? "lean3d_f32_gradwin_tma" : "lean3d_f32_gradwin";
             } else {
                 edf_lean_launch(p.inp[ii].order, p.gradient, grid, st, p, L, ii);
                 *name = p.gradient ? "lean3d_f32_grad" : "lean3d_f32";

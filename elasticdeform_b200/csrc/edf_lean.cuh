@@ -12,6 +12,7 @@
 #pragma once
 #include "edf_fast.cuh"
 #include <stdlib.h>
+#include <cuda.h>            // CUtensorMap (driver types only; the encoder is fetched at run time)
 
 #define EDF_LEAN_EPSF 1e-6f        // float-side threshold test; superset of EDF_FAST_EPS (2e-8)
 
@@ -302,6 +303,253 @@ edf_lean3d_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ E
     }
 }
 
+// =======================================================================================
+// Forward kernel, batched: U rows of a thread are processed together, phase by phase
+// (coordinates -> classification -> offsets / weights -> all loads -> FMAs -> stores), written
+// branch-free so that the U independent dependency chains interleave.  The per-voxel latency
+// chain (LDS -> 4 DFMA -> floor -> convert -> address -> LDG -> FFMA -> STG) is ~10x longer than
+// its issue time; with 16 warps per SM one voxel at a time left the issue slots 57-66 % idle.
+// Rare voxels (next to a rounding threshold, or out of range in a non-constant mode) are flagged
+// and redone afterwards by the single-voxel routine, which overwrites the output.
+// Mirror mapping of edge taps uses the single-reflection form, valid for extents >= 8.
+// =======================================================================================
+template <int ORDER>
+__device__ __noinline__ void edf_lean_forward_slow(const EdfParams& p, const EdfFastLaunch& L, int ii,
+                                                   int z, int y, int x, double inz, double iny, double inx,
+                                                   bool gate)
+{
+    int o[3] = {z, y, x};
+    double in[3] = {inz, iny, inx};
+    if (gate && (edf_near_half_integer(in[0]) || edf_near_half_integer(in[1]) || edf_near_half_integer(in[2]))) {
+        double dd[3];
+        edf_displacement_exact_cold<3>(p, o, dd);
+#pragma unroll
+        for (int h = 0; h < 3; ++h) in[h] = edf_source_coordinate<3, int>(p, o, h, dd[h]);
+    }
+    edf_fast_f32_one_input<3, ORDER, false>(p, L, ii, o, in);
+}
+
+// single-reflection mirror map (deform.c:796-810 for indices within one period of the border)
+__device__ __forceinline__ int edf_mirror1(int idx, int len)
+{
+    idx = idx < 0 ? -idx : idx;
+    return idx >= len ? 2 * len - 2 - idx : idx;
+}
+
+template <int ORDER, int U>
+__global__ void __launch_bounds__(EDF_FAST_THREADS, 2)
+edf_lean3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii)
+{
+    __shared__ EdfLeanSmem s;
+    constexpr int NT = ORDER + 1;
+    constexpr int NCHUNK = EDF_FAST_RY / EDF_FAST_M;
+    const int x0 = blockIdx.x * EDF_FAST_TX;
+    const int y0 = blockIdx.y * EDF_FAST_RY;
+    const int z0 = blockIdx.z * EDF_FAST_G;
+    edf_lean_tile_setup(p, s, z0, y0, x0);
+
+    const int tx = threadIdx.x & (EDF_FAST_TX - 1);
+    const int g = threadIdx.x >> 6;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = x0 + tx, z = z0 + g;
+    const int odz = (int)p.odim[0], ody = (int)p.odim[1], odx = (int)p.odim[2];
+    const bool tok = (x < odx) && (z < odz);
+    double wx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wx[k] = s.wx[tx][k];
+    const int sxrel = s.sx[tx] - s.sx[0];
+    const int nchunk = min(NCHUNK, (ody - y0 + EDF_FAST_M - 1) / EDF_FAST_M);
+    const bool gate = s.nonzero != 0;
+    const int nx = s.nx, sy_min = s.sy[0];
+    double (*Bw)[EDF_FAST_M][EDF_FAST_NC] = s.Bw[warp];
+
+    const EdfInputDesc& d = p.inp[ii];
+    const float* __restrict__ pin = (const float*)d.in;
+    float* __restrict__ pout = (float*)d.out;
+    const int lenz = (int)p.idim[0], leny = (int)p.idim[1], lenx = (int)p.idim[2];
+    const double limz = p.idim_m1[0], limy = p.idim_m1[1], limx = p.idim_m1[2];
+    const int isz = L.istr_e[ii][0], isy = L.istr_e[ii][1];
+    const int osy = L.ostr_e[ii][1];
+    const int64_t obase_zx = (int64_t)z * L.ostr_e[ii][0] + (int64_t)x * L.ostr_e[ii][2];
+    const bool affine = p.has_affine != 0;
+    const bool cmode = d.mode == EDF_MODE_CONSTANT;
+    const float cvalf = __uint_as_float((uint32_t)L.cval_bits[ii]);
+    const double bz = xadd((double)z, p.ooff_d[0]);
+    const double bx = xadd((double)x, p.ooff_d[2]);
+    const double offy = p.ooff_d[1];
+
+    for (int c = 0; c < nchunk; ++c) {
+        for (int e = lane; e < 3 * EDF_FAST_M * nx; e += 32) {
+            const int jx = e % nx;
+            const int m = (e / nx) % EDF_FAST_M;
+            const int h = e / (nx * EDF_FAST_M);
+            const int row = c * EDF_FAST_M + m;
+            const int r0 = s.sy[row] - sy_min;
+            double b = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b = fma(s.A[h][g][r0 + j][jx], s.wy[row][j], b);
+            Bw[h][m][jx] = b;
+        }
+        __syncwarp();
+        if (tok) {
+#pragma unroll 1
+            for (int m0 = 0; m0 < EDF_FAST_M; m0 += U) {
+                const int yb = y0 + c * EDF_FAST_M + m0;
+                if (yb >= ody) break;
+                double inz[U], iny[U], inx[U];
+                int stz[U], sty[U], stx[U];
+                float fz[U], fy[U], fx[U];
+                bool valid[U], cst[U], slow[U];
+                bool any_ex = false;
+                // ---- phase 1: coordinates and classification (branch-free)
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int m = m0 + u;
+                    const int y = yb + u;
+                    valid[u] = y < ody;
+                    double dz = 0.0, dy = 0.0, dx = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        dz = fma(Bw[0][m][sxrel + k], wx[k], dz);
+                        dy = fma(Bw[1][m][sxrel + k], wx[k], dy);
+                        dx = fma(Bw[2][m][sxrel + k], wx[k], dx);
+                    }
+                    if (!affine) {
+                        inz[u] = xadd(bz, dz);
+                        iny[u] = xadd(xadd((double)y, offy), dy);
+                        inx[u] = xadd(bx, dx);
+                    } else {
+                        const int o[3] = {z, y, x};
+                        inz[u] = edf_source_coordinate<3, int>(p, o, 0, dz);
+                        iny[u] = edf_source_coordinate<3, int>(p, o, 1, dy);
+                        inx[u] = edf_source_coordinate<3, int>(p, o, 2, dx);
+                    }
+                    // clamp into the volume: out-of-range voxels get a harmless in-range address
+                    double cz = fmin(fmax(inz[u], 0.0), limz);
+                    double cy = fmin(fmax(iny[u], 0.0), limy);
+                    double cx = fmin(fmax(inx[u], 0.0), limx);
+                    const bool inr = (cz == inz[u]) & (cy == iny[u]) & (cx == inx[u]);   // false for NaN too
+                    bool mapped_danger = false, nanflag = false;
+                    if (!cmode && !inr) {
+                        // boundary map of the out-of-range axes, out of line (deform.c:47-128); the mapped
+                        // coordinate is in [0, len-1] (reflect: possibly in (-1, 0), handled by the mirror taps)
+                        if (cz != inz[u]) { mapped_danger |= edf_near_half_integer(inz[u]); cz = edf_map_coordinate_cold(inz[u], lenz, d.mode); }
+                        if (cy != iny[u]) { mapped_danger |= edf_near_half_integer(iny[u]); cy = edf_map_coordinate_cold(iny[u], leny, d.mode); }
+                        if (cx != inx[u]) { mapped_danger |= edf_near_half_integer(inx[u]); cx = edf_map_coordinate_cold(inx[u], lenx, d.mode); }
+                        if (!((cz > -1.0) & (cy > -1.0) & (cx > -1.0))) { nanflag = true; cz = cy = cx = 0.0; }   // NaN
+                    }
+                    const double flz = (ORDER & 1) ? floor(cz) : floor(xadd(cz, 0.5));
+                    const double fly = (ORDER & 1) ? floor(cy) : floor(xadd(cy, 0.5));
+                    const double flx = (ORDER & 1) ? floor(cx) : floor(xadd(cx, 0.5));
+                    fz[u] = (float)xsub(cz, flz);
+                    fy[u] = (float)xsub(cy, fly);
+                    fx[u] = (float)xsub(cx, flx);
+                    stz[u] = (int)flz - ORDER / 2;
+                    sty[u] = (int)fly - ORDER / 2;
+                    stx[u] = (int)flx - ORDER / 2;
+                    bool danger;
+                    if (ORDER & 1)
+                        danger = (fz[u] < EDF_LEAN_EPSF) | (fz[u] > 1.0f - EDF_LEAN_EPSF) | (fy[u] < EDF_LEAN_EPSF) |
+                                 (fy[u] > 1.0f - EDF_LEAN_EPSF) | (fx[u] < EDF_LEAN_EPSF) | (fx[u] > 1.0f - EDF_LEAN_EPSF);
+                    else
+                        danger = (fabsf(fz[u]) < EDF_LEAN_EPSF) | (fabsf(fz[u]) > 0.5f - EDF_LEAN_EPSF) |
+                                 (fabsf(fy[u]) < EDF_LEAN_EPSF) | (fabsf(fy[u]) > 0.5f - EDF_LEAN_EPSF) |
+                                 (fabsf(fx[u]) < EDF_LEAN_EPSF) | (fabsf(fx[u]) > 0.5f - EDF_LEAN_EPSF);
+                    danger |= mapped_danger;
+                    // in range (or mapped into range): only thresholds matter.  Out of range in 'constant' mode:
+                    // cval, unless the voxel misses the volume by less than the re-evaluation threshold.
+                    bool nearmiss = false;
+                    if (cmode) {
+                        const double qz = fabs(xsub(inz[u], cz)), qy = fabs(xsub(iny[u], cy)), qx = fabs(xsub(inx[u], cx));
+                        nearmiss = ((qz > 0.0) & (qz < EDF_FAST_EPS)) | ((qy > 0.0) & (qy < EDF_FAST_EPS)) |
+                                   ((qx > 0.0) & (qx < EDF_FAST_EPS));
+                    }
+                    slow[u] = valid[u] & ((gate & ((inr | !cmode) ? danger : nearmiss)) | nanflag);
+                    cst[u] = valid[u] & !inr & cmode & !slow[u];
+                    any_ex |= (stx[u] < 0) | (stx[u] + ORDER >= lenx);
+                }
+                // ---- phase 2: tap offsets (single-reflection mirror at the edges) and weights
+                float t[U];
+                const bool warp_ex = __any_sync(__activemask(), any_ex);
+                if (ORDER == 0) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        t[u] = __ldg(pin + (edf_mirror1(stz[u], lenz) * isz + edf_mirror1(sty[u], leny) * isy +
+                                            edf_mirror1(stx[u], lenx)));
+                } else {
+                    int oz[U][NT], oy[U][NT];
+                    float wz[U][NT], wy[U][NT], wxf[U][NT];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) {
+                            oz[u][i] = edf_mirror1(stz[u] + i, lenz) * isz;
+                            oy[u][i] = edf_mirror1(sty[u] + i, leny) * isy;
+                        }
+                        edf_bspline_weights_f32<ORDER>(fz[u], wz[u]);
+                        edf_bspline_weights_f32<ORDER>(fy[u], wy[u]);
+                        edf_bspline_weights_f32<ORDER>(fx[u], wxf[u]);
+                    }
+                    if (!warp_ex) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            float acc = 0.f;
+#pragma unroll
+                            for (int i = 0; i < NT; ++i) {
+                                float ti = 0.f;
+#pragma unroll
+                                for (int j = 0; j < NT; ++j) {
+                                    const float* r = pin + (oz[u][i] + oy[u][j] + stx[u]);
+                                    float tj = __ldg(r) * wxf[u][0];
+#pragma unroll
+                                    for (int k = 1; k < NT; ++k) tj = fmaf(__ldg(r + k), wxf[u][k], tj);
+                                    ti = (j == 0) ? tj * wy[u][0] : fmaf(tj, wy[u][j], ti);
+                                }
+                                acc = (i == 0) ? ti * wz[u][0] : fmaf(ti, wz[u][i], acc);
+                            }
+                            t[u] = acc;
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            int oxk[NT];
+#pragma unroll
+                            for (int k = 0; k < NT; ++k) oxk[k] = edf_mirror1(stx[u] + k, lenx);
+                            float acc = 0.f;
+#pragma unroll
+                            for (int i = 0; i < NT; ++i) {
+                                float ti = 0.f;
+#pragma unroll
+                                for (int j = 0; j < NT; ++j) {
+                                    const float* r = pin + (oz[u][i] + oy[u][j]);
+                                    float tj = __ldg(r + oxk[0]) * wxf[u][0];
+#pragma unroll
+                                    for (int k = 1; k < NT; ++k) tj = fmaf(__ldg(r + oxk[k]), wxf[u][k], tj);
+                                    ti = (j == 0) ? tj * wy[u][0] : fmaf(tj, wy[u][j], ti);
+                                }
+                                acc = (i == 0) ? ti * wz[u][0] : fmaf(ti, wz[u][i], acc);
+                            }
+                            t[u] = acc;
+                        }
+                    }
+                }
+                // ---- phase 3: stores; flagged voxels are redone by the single-voxel routine
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (valid[u]) {
+                        float* po = pout + (obase_zx + (int64_t)(yb + u) * osy);
+                        *po = cst[u] ? cvalf : t[u];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (slow[u]) edf_lean_forward_slow<ORDER>(p, L, ii, z, yb + u, x, inz[u], iny[u], inx[u], gate);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 static bool edf_lean_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii)
 {
     if (p.naxis != 3) return false;
@@ -309,16 +557,27 @@ static bool edf_lean_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii
     if (d.in_dtype != EDF_F32 || d.out_dtype != EDF_F32) return false;
     if (d.nstep_rank != 0) return false;
     if (L.istr_e[ii][2] != 1) return false;
+    for (int a = 0; a < 3; ++a)
+        if (p.idim[a] < 8) return false;      // single-reflection mirror map of the batched forward kernel
     return true;
 }
 
 static void edf_lean_launch(int order, int gradient, dim3 grid, cudaStream_t st, const EdfParams& p,
                             const EdfFastLaunch& L, int ii)
 {
-    static int variant = -1;                  // experiment knob: occupancy target of the order-3 forward kernel
+    static int variant = -1;                  // experiment knob: 1 = one voxel at a time (previous forward kernel)
     if (variant < 0) { const char* e = getenv("EDF_LEAN_VARIANT"); variant = e ? atoi(e) : 0; }
-    if (order == 3 && !gradient && variant == 1) { edf_lean3d_kernel<3, false, 3><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); return; }
-    if (order == 3 && !gradient && variant == 2) { edf_lean3d_kernel<3, false, 4><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); return; }
+    if (!gradient && variant != 1) {
+        switch (order) {
+        case 0: edf_lean3d_fwd_kernel<0, 4><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
+        case 1: edf_lean3d_fwd_kernel<1, 4><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
+        case 2: edf_lean3d_fwd_kernel<2, 2><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
+        case 3: edf_lean3d_fwd_kernel<3, 2><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
+        case 4: edf_lean3d_fwd_kernel<4, 1><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
+        default: edf_lean3d_fwd_kernel<5, 1><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
+        }
+        return;
+    }
 #define EDF_LEAN_CASE(O)                                                                       \
     case O:                                                                                    \
         if (gradient) edf_lean3d_kernel<O, true><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii);  \
@@ -372,7 +631,7 @@ struct EdfGradWinSmem {
     int    wmin[3], pad_;
     double A[3][EDF_GW_G][EDF_GW_NC][EDF_GW_NC];
     double Bw[EDF_GW_WARPS][3][EDF_GW_MR][EDF_GW_NC];
-    __align__(16) int win[EDF_GW_WZ * EDF_GW_WY * EDF_GW_WX];
+    __align__(128) int win[EDF_GW_WZ * EDF_GW_WY * EDF_GW_WX];   // 128-byte aligned: TMA source
 };
 
 // un-mapped source coordinates of voxel (z, y, x) from the warp's B table (same arithmetic as the
@@ -400,11 +659,14 @@ __device__ __forceinline__ void edf_gw_coords(const EdfParams& p, const double (
     }
 }
 
-template <int ORDER, bool VEC>
+// FLUSH: 0 = scalar atomics, 1 = 16-byte vector atomics, 2 = one TMA tensor reduce-add of the whole
+// window box per chunk (cp.reduce.async.bulk.tensor.3d ... .add, SASS UTMAREDG)
+template <int ORDER, int FLUSH>
 __global__ void __launch_bounds__(EDF_GW_THREADS, 2)
-edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii)
+edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii,
+                          const __grid_constant__ CUtensorMap tmap)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     EdfGradWinSmem& s = *reinterpret_cast<EdfGradWinSmem*>(smem_raw);
     constexpr int NT = ORDER + 1;
     constexpr int NCHUNK = EDF_FAST_RY / EDF_FAST_M;
@@ -616,7 +878,28 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
             }
             __syncthreads();
             // ---- flush: every touched window cell once, coalesced along x, and re-zero
-            if (VEC) {
+            if (FLUSH == 2) {
+                // convert the fixed-point window to float in place, hand the whole box to the TMA unit
+                // (out-of-volume cells are clipped by the tensor map), wait for the read, re-zero
+                for (int q = tid; q < NWIN / 4; q += EDF_GW_THREADS) {
+                    const int4 v = reinterpret_cast<int4*>(s.win)[q];
+                    reinterpret_cast<float4*>(s.win)[q] = make_float4((float)v.x * inv_scale, (float)v.y * inv_scale,
+                                                                     (float)v.z * inv_scale, (float)v.w * inv_scale);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                if (tid == 0) {
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(s.win);
+                    asm volatile(
+                        "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                        :: "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(wx0), "r"(wy0), "r"(wz0), "r"(src) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                __syncthreads();
+                for (int q = tid; q < NWIN / 4; q += EDF_GW_THREADS)
+                    reinterpret_cast<int4*>(s.win)[q] = make_int4(0, 0, 0, 0);
+            } else if (FLUSH == 1) {
                 for (int q = tid; q < NWIN / 4; q += EDF_GW_THREADS) {
                     int4 v = reinterpret_cast<int4*>(s.win)[q];
                     if ((v.x | v.y | v.z | v.w) != 0) {
@@ -658,6 +941,27 @@ static bool edf_gradwin_eligible(const EdfParams& p)
     return p.naxis == 3 && edf_fast_ctrl_span_ok(p, 2, EDF_GW_TX, EDF_GW_NC) && edf_fast_ctrl_span_ok(p, 1, EDF_FAST_RY, EDF_GW_NC);
 }
 
+// cuTensorMapEncodeTiled, fetched from the driver at run time (no link-time dependency on libcuda)
+typedef CUresult (*edf_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static edf_tmap_encode_fn edf_tmap_encoder()
+{
+    static edf_tmap_encode_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (edf_tmap_encode_fn)ptr;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
 static int edf_lean_launch_gradwin(int order, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii)
 {
     dim3 grid;
@@ -666,28 +970,46 @@ static int edf_lean_launch_gradwin(int order, cudaStream_t st, const EdfParams& 
     grid.z = (unsigned)((p.odim[0] + EDF_GW_G - 1) / EDF_GW_G);
     const size_t smem = sizeof(EdfGradWinSmem);
     if (!g_gradwin_configured) {
-#define EDF_GW_ATTR(O)                                                                                              \
-    cudaFuncSetAttribute(edf_lean3d_gradwin_kernel<O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    cudaFuncSetAttribute(edf_lean3d_gradwin_kernel<O, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+#define EDF_GW_ATTR(O)                                                                                           \
+    cudaFuncSetAttribute(edf_lean3d_gradwin_kernel<O, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaFuncSetAttribute(edf_lean3d_gradwin_kernel<O, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    cudaFuncSetAttribute(edf_lean3d_gradwin_kernel<O, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
         EDF_GW_ATTR(0); EDF_GW_ATTR(1); EDF_GW_ATTR(2); EDF_GW_ATTR(3); EDF_GW_ATTR(4); EDF_GW_ATTR(5);
 #undef EDF_GW_ATTR
         if (cudaGetLastError() != cudaSuccess) return -1;
         g_gradwin_configured = true;
     }
-    // 16-byte vector flush needs 16-byte aligned rows of dX
+    // 16-byte vector flush / TMA need 16-byte aligned rows of dX
     const bool vec = ((uintptr_t)p.inp[ii].in % 16 == 0) && (L.istr_e[ii][0] % 4 == 0) && (L.istr_e[ii][1] % 4 == 0);
-#define EDF_GW_CASE(O)                                                                                     \
-    case O:                                                                                                \
-        if (vec) edf_lean3d_gradwin_kernel<O, true><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii);          \
-        else     edf_lean3d_gradwin_kernel<O, false><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii);         \
+    static int want_tma = -1;
+    if (want_tma < 0) { const char* e = getenv("EDF_GRADWIN_TMA"); want_tma = (e && *e && *e != '0') ? 1 : 0; }
+    int flush = vec ? 1 : 0;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (vec && want_tma && edf_tmap_encoder()) {
+        const cuuint64_t gdim[3] = {(cuuint64_t)p.idim[2], (cuuint64_t)p.idim[1], (cuuint64_t)p.idim[0]};
+        const cuuint64_t gstr[2] = {(cuuint64_t)L.istr_e[ii][1] * 4, (cuuint64_t)L.istr_e[ii][0] * 4};
+        const cuuint32_t box[3] = {EDF_GW_WX, EDF_GW_WY, EDF_GW_WZ};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        if (edf_tmap_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.inp[ii].in, gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            flush = 2;
+    }
+#define EDF_GW_CASE(O)                                                                                         \
+    case O:                                                                                                    \
+        if (flush == 2)      edf_lean3d_gradwin_kernel<O, 2><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii, tmap); \
+        else if (flush == 1) edf_lean3d_gradwin_kernel<O, 1><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii, tmap); \
+        else                 edf_lean3d_gradwin_kernel<O, 0><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii, tmap); \
         break;
     switch (order) {
         EDF_GW_CASE(0) EDF_GW_CASE(1) EDF_GW_CASE(2) EDF_GW_CASE(3) EDF_GW_CASE(4)
     default:
-        if (vec) edf_lean3d_gradwin_kernel<5, true><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii);
-        else     edf_lean3d_gradwin_kernel<5, false><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii);
+        if (flush == 2)      edf_lean3d_gradwin_kernel<5, 2><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii, tmap);
+        else if (flush == 1) edf_lean3d_gradwin_kernel<5, 1><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii, tmap);
+        else                 edf_lean3d_gradwin_kernel<5, 0><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii, tmap);
         break;
     }
 #undef EDF_GW_CASE
-    return 0;
+    return flush == 2 ? 2 : 0;
 }

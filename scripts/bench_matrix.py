@@ -48,6 +48,25 @@ def run(name, shapes, dtypes, orders, points, sigma, axis=None, mode='constant',
                          Mvox_s=round(nvox / t / 1e3, 1))
     print(json.dumps({"config": name, **out}), flush=True)
 
+def prefilter_times(shape=(256, 256, 256), order=3, reps=5):
+    rng = np.random.default_rng(1)
+    x = torch.from_numpy(rng.random(shape, dtype=np.float32)).to(dev)
+    out = torch.empty_like(x)
+    st = torch.cuda.current_stream(dev)
+    res = {}
+    for adj in (False, True):
+        for ax in range(len(shape)):
+            ts = []
+            for r in range(reps + 2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                dg._spline_filter1d_device(lib, x, out, ax, order, adjoint=adj)
+                e1.record(st); torch.cuda.synchronize()
+                if r >= 2: ts.append(e0.elapsed_time(e1))
+            res["%s_axis%d_ms" % ("adjoint" if adj else "prefilter", ax)] = round(float(np.median(ts)), 4)
+    print(json.dumps({"config": "prefilter %s order %d" % (str(shape), order), **res}), flush=True)
+
+
 if __name__ == "__main__":
     S = (256, 256, 256)
     for o in (0, 1, 3):
@@ -57,3 +76,5 @@ if __name__ == "__main__":
     run("cfg5 32x128^3 f32 o1 axis=(1,2,3)", [(32, 128, 128, 128)], ['float32'], [1], (5, 5, 5), 8.0, axis=(1, 2, 3), reps=10)
     run("cfg1 200x300 f32 o3 reflect", [(200, 300)], ['float32'], [3], (3, 3), 25.0, mode='reflect')
     run("256^3 f32 order 3 mirror", [S], ['float32'], [3], (5, 5, 5), 8.0, mode='mirror', reps=10)
+    run("256^3 f32 order 1 nearest", [S], ['float32'], [1], (5, 5, 5), 8.0, mode='nearest', reps=10)
+    prefilter_times()
