@@ -172,27 +172,60 @@ edf_line_filter_kernel(const __grid_constant__ EdfLineParams p)
     }
     __syncthreads();
 
-    const int64_t total = (int64_t)nl * p.n;
-    for (int64_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        int l; int64_t i;
-        if (p.line_fastest) { l = (int)(idx / p.n); i = idx % p.n; }
-        else                { i = idx / nl;        l = (int)(idx % nl); }
-        sbuf[(size_t)l * p.ld + i] = edf_load(p.in + in_off[l] + i * p.in_lstr, p.in_dtype);
+    // ---- stage the lines as doubles (coalesced in either orientation, no per-element div/mod)
+    const int n = (int)p.n, ld = p.ld;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const bool f32 = p.in_dtype == EDF_F32, f64 = p.in_dtype == EDF_F64;
+    if (p.line_fastest) {
+        for (int l = warp; l < nl; l += nwarps) {
+            const char* src = p.in + in_off[l];
+            double* dst = sbuf + (size_t)l * ld;
+            for (int i = lane; i < n; i += 32) {
+                const char* q = src + (int64_t)i * p.in_lstr;
+                dst[i] = f32 ? (double)*(const float*)q : (f64 ? *(const double*)q : edf_load(q, p.in_dtype));
+            }
+        }
+    } else {
+        for (int i = warp; i < n; i += nwarps) {
+            const int64_t io = (int64_t)i * p.in_lstr;
+            for (int l = lane; l < nl; l += 32) {
+                const char* q = p.in + in_off[l] + io;
+                sbuf[(size_t)l * ld + i] = f32 ? (double)*(const float*)q : (f64 ? *(const double*)q : edf_load(q, p.in_dtype));
+            }
+        }
     }
     __syncthreads();
 
     for (int l = threadIdx.x; l < nl; l += blockDim.x) {
-        double* c = sbuf + (size_t)l * p.ld;
+        double* c = sbuf + (size_t)l * ld;
         if (p.adjoint) edf_prefilter_adjoint_line(c, p.n, p.f);
         else           edf_prefilter_line(c, p.n, p.f);
     }
     __syncthreads();
 
-    for (int64_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        int l; int64_t i;
-        if (p.line_fastest) { l = (int)(idx / p.n); i = idx % p.n; }
-        else                { i = idx / nl;        l = (int)(idx % nl); }
-        edf_store_cast(p.out + out_off[l] + i * p.out_lstr, p.out_dtype, sbuf[(size_t)l * p.ld + i]);
+    const bool o32 = p.out_dtype == EDF_F32, o64 = p.out_dtype == EDF_F64;
+    if (p.line_fastest) {
+        for (int l = warp; l < nl; l += nwarps) {
+            char* dstp = p.out + out_off[l];
+            const double* src = sbuf + (size_t)l * ld;
+            for (int i = lane; i < n; i += 32) {
+                char* q = dstp + (int64_t)i * p.out_lstr;
+                if (o32) *(float*)q = (float)src[i];
+                else if (o64) *(double*)q = src[i];
+                else edf_store_cast(q, p.out_dtype, src[i]);
+            }
+        }
+    } else {
+        for (int i = warp; i < n; i += nwarps) {
+            const int64_t oo = (int64_t)i * p.out_lstr;
+            for (int l = lane; l < nl; l += 32) {
+                char* q = p.out + out_off[l] + oo;
+                const double v = sbuf[(size_t)l * ld + i];
+                if (o32) *(float*)q = (float)v;
+                else if (o64) *(double*)q = v;
+                else edf_store_cast(q, p.out_dtype, v);
+            }
+        }
     }
 }
 
@@ -264,7 +297,7 @@ static int run_line_filter(const edf_array* input, const edf_array* output, int 
         return edf_fail(EDF_ERR_MEMORY, "line of %lld elements does not fit in shared memory",
                         (long long)p.n);
     // keep >= ~4 CTAs per SM worth of lines when the problem is large enough
-    int64_t Lcap = 64;
+    int64_t Lcap = 32;
     if (L > Lcap) L = Lcap;
     if (L > p.nlines) L = p.nlines;
     p.lines_per_block = (int)L;

@@ -12,7 +12,6 @@
 #pragma once
 #include "edf_fast.cuh"
 #include <stdlib.h>
-#include <cuda.h>            // CUtensorMap (driver types only; the encoder is fetched at run time)
 
 #define EDF_LEAN_EPSF 1e-6f        // float-side threshold test; superset of EDF_FAST_EPS (2e-8)
 
@@ -629,6 +628,7 @@ struct EdfGradWinSmem {
     int    sx[EDF_GW_TX];
     int    ny, nx, nonzero, gmax_bits;
     int    wmin[3], pad_;
+    unsigned rowmask[(EDF_GW_WZ * EDF_GW_WY + 31) / 32 + 1];   // window rows holding contributions (TMA flush)
     double A[3][EDF_GW_G][EDF_GW_NC][EDF_GW_NC];
     double Bw[EDF_GW_WARPS][3][EDF_GW_MR][EDF_GW_NC];
     __align__(128) int win[EDF_GW_WZ * EDF_GW_WY * EDF_GW_WX];   // 128-byte aligned: TMA source
@@ -659,12 +659,14 @@ __device__ __forceinline__ void edf_gw_coords(const EdfParams& p, const double (
     }
 }
 
-// FLUSH: 0 = scalar atomics, 1 = 16-byte vector atomics, 2 = one TMA tensor reduce-add of the whole
-// window box per chunk (cp.reduce.async.bulk.tensor.3d ... .add, SASS UTMAREDG)
+// FLUSH: 0 = scalar atomics, 1 = 16-byte vector atomics, 2 = TMA bulk reduce-add per window row
+// (cp.reduce.async.bulk ... .add.f32, SASS UBLKRED).  A single tensor-map reduce of the whole box
+// (cp.reduce.async.bulk.tensor.3d, UTMAREDG) would be the natural form, but every tensor-map TMA
+// instruction traps with cudaErrorIllegalInstruction on this pool's B200 boxes, also in the
+// stand-alone reproducer scripts/experiments/tma_reduce_test.cu, so the row form is used.
 template <int ORDER, int FLUSH>
 __global__ void __launch_bounds__(EDF_GW_THREADS, 2)
-edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii,
-                          const __grid_constant__ CUtensorMap tmap)
+edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     EdfGradWinSmem& s = *reinterpret_cast<EdfGradWinSmem*>(smem_raw);
@@ -688,6 +690,7 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
         edf_fast_ctrl_entry(p, 0, min((int64_t)(z0 + t), p.odim[0] - 1), s.wz[t], &s.sz[t]);
     }
     for (int e = tid; e < NWIN; e += EDF_GW_THREADS) s.win[e] = 0;
+    if (tid < (EDF_GW_WZ * EDF_GW_WY + 31) / 32 + 1) s.rowmask[tid] = 0;
     __syncthreads();
     {
         const int sy_min0 = s.sy[0], sx_min0 = s.sx[0];
@@ -879,26 +882,44 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
             __syncthreads();
             // ---- flush: every touched window cell once, coalesced along x, and re-zero
             if (FLUSH == 2) {
-                // convert the fixed-point window to float in place, hand the whole box to the TMA unit
-                // (out-of-volume cells are clipped by the tensor map), wait for the read, re-zero
+                // TMA flush: convert the fixed-point window to float in place, then one bulk reduce-add
+                // (cp.reduce.async.bulk ... .add.f32, SASS UBLKRED) per window ROW that holds contributions:
+                // a row is 52 contiguous floats both in shared memory and in dX.
+                constexpr int GPR = EDF_GW_WX / 4;                 // 16-byte groups per row
                 for (int q = tid; q < NWIN / 4; q += EDF_GW_THREADS) {
                     const int4 v = reinterpret_cast<int4*>(s.win)[q];
-                    reinterpret_cast<float4*>(s.win)[q] = make_float4((float)v.x * inv_scale, (float)v.y * inv_scale,
-                                                                     (float)v.z * inv_scale, (float)v.w * inv_scale);
+                    if ((v.x | v.y | v.z | v.w) != 0) {
+                        const int row = q / GPR;
+                        atomicOr(&s.rowmask[row >> 5], 1u << (row & 31));
+                        reinterpret_cast<float4*>(s.win)[q] = make_float4((float)v.x * inv_scale, (float)v.y * inv_scale,
+                                                                         (float)v.z * inv_scale, (float)v.w * inv_scale);
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncthreads();
-                if (tid == 0) {
-                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(s.win);
-                    asm volatile(
-                        "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
-                        :: "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(wx0), "r"(wy0), "r"(wz0), "r"(src) : "memory");
+                bool issued = false;
+                for (int row = tid; row < EDF_GW_WZ * EDF_GW_WY; row += EDF_GW_THREADS) {
+                    if (!((s.rowmask[row >> 5] >> (row & 31)) & 1u)) continue;
+                    const int iz = row / EDF_GW_WY, iy = row % EDF_GW_WY;
+                    const int xs = max(wx0, 0), xe = min(wx0 + EDF_GW_WX, lenx);   // lenx % 4 == 0 (host-checked)
+                    // rows outside the volume never receive contributions (their voxels take the fallback)
+                    float* dst = pdx + ((wz0 + iz) * isz + (wy0 + iy) * isy + xs);
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(s.win + row * EDF_GW_WX + (xs - wx0));
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                                 :: "l"(dst), "r"(src), "r"((uint32_t)((xe - xs) * 4)) : "memory");
+                    issued = true;
+                }
+                if (issued) {
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 }
                 __syncthreads();
-                for (int q = tid; q < NWIN / 4; q += EDF_GW_THREADS)
-                    reinterpret_cast<int4*>(s.win)[q] = make_int4(0, 0, 0, 0);
+                for (int q = tid; q < NWIN / 4; q += EDF_GW_THREADS) {
+                    const int row = q / GPR;
+                    if ((s.rowmask[row >> 5] >> (row & 31)) & 1u) reinterpret_cast<int4*>(s.win)[q] = make_int4(0, 0, 0, 0);
+                }
+                __syncthreads();
+                if (tid < (EDF_GW_WZ * EDF_GW_WY + 31) / 32 + 1) s.rowmask[tid] = 0;
             } else if (FLUSH == 1) {
                 for (int q = tid; q < NWIN / 4; q += EDF_GW_THREADS) {
                     int4 v = reinterpret_cast<int4*>(s.win)[q];
@@ -941,27 +962,6 @@ static bool edf_gradwin_eligible(const EdfParams& p)
     return p.naxis == 3 && edf_fast_ctrl_span_ok(p, 2, EDF_GW_TX, EDF_GW_NC) && edf_fast_ctrl_span_ok(p, 1, EDF_FAST_RY, EDF_GW_NC);
 }
 
-// cuTensorMapEncodeTiled, fetched from the driver at run time (no link-time dependency on libcuda)
-typedef CUresult (*edf_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static edf_tmap_encode_fn edf_tmap_encoder()
-{
-    static edf_tmap_encode_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = (edf_tmap_encode_fn)ptr;
-        cudaGetLastError();
-    }
-    return fn;
-}
-
 static int edf_lean_launch_gradwin(int order, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii)
 {
     dim3 grid;
@@ -984,30 +984,19 @@ static int edf_lean_launch_gradwin(int order, cudaStream_t st, const EdfParams& 
     static int want_tma = -1;
     if (want_tma < 0) { const char* e = getenv("EDF_GRADWIN_TMA"); want_tma = (e && *e && *e != '0') ? 1 : 0; }
     int flush = vec ? 1 : 0;
-    CUtensorMap tmap;
-    memset(&tmap, 0, sizeof(tmap));
-    if (vec && want_tma && edf_tmap_encoder()) {
-        const cuuint64_t gdim[3] = {(cuuint64_t)p.idim[2], (cuuint64_t)p.idim[1], (cuuint64_t)p.idim[0]};
-        const cuuint64_t gstr[2] = {(cuuint64_t)L.istr_e[ii][1] * 4, (cuuint64_t)L.istr_e[ii][0] * 4};
-        const cuuint32_t box[3] = {EDF_GW_WX, EDF_GW_WY, EDF_GW_WZ};
-        const cuuint32_t estr[3] = {1, 1, 1};
-        if (edf_tmap_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)p.inp[ii].in, gdim, gstr, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
-            flush = 2;
-    }
+    if (vec && want_tma && p.idim[2] % 4 == 0) flush = 2;
 #define EDF_GW_CASE(O)                                                                                         \
     case O:                                                                                                    \
-        if (flush == 2)      edf_lean3d_gradwin_kernel<O, 2><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii, tmap); \
-        else if (flush == 1) edf_lean3d_gradwin_kernel<O, 1><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii, tmap); \
-        else                 edf_lean3d_gradwin_kernel<O, 0><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii, tmap); \
+        if (flush == 2)      edf_lean3d_gradwin_kernel<O, 2><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii); \
+        else if (flush == 1) edf_lean3d_gradwin_kernel<O, 1><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii); \
+        else                 edf_lean3d_gradwin_kernel<O, 0><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii); \
         break;
     switch (order) {
         EDF_GW_CASE(0) EDF_GW_CASE(1) EDF_GW_CASE(2) EDF_GW_CASE(3) EDF_GW_CASE(4)
     default:
-        if (flush == 2)      edf_lean3d_gradwin_kernel<5, 2><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii, tmap);
-        else if (flush == 1) edf_lean3d_gradwin_kernel<5, 1><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii, tmap);
-        else                 edf_lean3d_gradwin_kernel<5, 0><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii, tmap);
+        if (flush == 2)      edf_lean3d_gradwin_kernel<5, 2><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii);
+        else if (flush == 1) edf_lean3d_gradwin_kernel<5, 1><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii);
+        else                 edf_lean3d_gradwin_kernel<5, 0><<<grid, EDF_GW_THREADS, smem, st>>>(p, L, ii);
         break;
     }
 #undef EDF_GW_CASE
