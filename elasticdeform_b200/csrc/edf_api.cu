@@ -119,15 +119,59 @@ extern "C" int edf_deform_grid_grad(const edf_problem* problem, void* stream)
     return run_problem(problem, 1, (cudaStream_t)stream);
 }
 
+// Batch of independent problems.  A small volume (e.g. a 64^3 crop = 64 CTAs) cannot fill 148 SMs,
+// so the problems are spread over a few internal streams forked from / joined to the caller's
+// stream with events: kernels of different volumes run concurrently, ordering with respect to the
+// caller's stream is preserved, nothing synchronises the host.
+#define EDF_BATCH_STREAMS 4
+struct EdfBatchStreams {
+    int device = -1;
+    cudaStream_t s[EDF_BATCH_STREAMS] = {};
+    cudaEvent_t fork = nullptr, join[EDF_BATCH_STREAMS] = {};
+};
+static thread_local EdfBatchStreams g_batch;
+
+static int batch_streams_ready()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (g_batch.device == dev) return 1;
+    // (re)create for this device; a thread that hops devices simply gets a new set
+    for (int i = 0; i < EDF_BATCH_STREAMS; ++i) {
+        if (cudaStreamCreateWithFlags(&g_batch.s[i], cudaStreamNonBlocking) != cudaSuccess) return 0;
+        if (cudaEventCreateWithFlags(&g_batch.join[i], cudaEventDisableTiming) != cudaSuccess) return 0;
+    }
+    if (cudaEventCreateWithFlags(&g_batch.fork, cudaEventDisableTiming) != cudaSuccess) return 0;
+    g_batch.device = dev;
+    return 1;
+}
+
 extern "C" int edf_deform_grid_batch(const edf_problem* problems, int32_t n, int32_t gradient,
                                      void* stream)
 {
     if (n < 0 || (n > 0 && !problems)) return edf_fail(EDF_ERR_RUNTIME, "invalid batch");
-    for (int i = 0; i < n; ++i) {
-        int rc = run_problem(&problems[i], gradient ? 1 : 0, (cudaStream_t)stream);
-        if (rc != EDF_OK) return rc;
+    cudaStream_t user = (cudaStream_t)stream;
+    if (n < 2 || !batch_streams_ready()) {
+        cudaGetLastError();
+        for (int i = 0; i < n; ++i) {
+            int rc = run_problem(&problems[i], gradient ? 1 : 0, user);
+            if (rc != EDF_OK) return rc;
+        }
+        return EDF_OK;
     }
-    return EDF_OK;
+    const int ns = n < EDF_BATCH_STREAMS ? n : EDF_BATCH_STREAMS;
+    cudaEventRecord(g_batch.fork, user);
+    for (int k = 0; k < ns; ++k) cudaStreamWaitEvent(g_batch.s[k], g_batch.fork, 0);
+    int rc = EDF_OK;
+    for (int i = 0; i < n && rc == EDF_OK; ++i)
+        rc = run_problem(&problems[i], gradient ? 1 : 0, g_batch.s[i % ns]);
+    for (int k = 0; k < ns; ++k) {                 // always join, also after an error
+        cudaEventRecord(g_batch.join[k], g_batch.s[k]);
+        cudaStreamWaitEvent(user, g_batch.join[k], 0);
+    }
+    if (rc == EDF_OK && cudaGetLastError() != cudaSuccess)
+        return edf_fail(EDF_ERR_CUDA, "batch stream fork/join failed");
+    return rc;
 }
 
 // ----------------------------------------------------------------------------

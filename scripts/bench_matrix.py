@@ -48,6 +48,37 @@ def run(name, shapes, dtypes, orders, points, sigma, axis=None, mode='constant',
                          Mvox_s=round(nvox / t / 1e3, 1))
     print(json.dumps({"config": name, **out}), flush=True)
 
+def cfg4_batch(nb=64, reps=5):
+    """BASELINE config 4 on one GPU: nb volumes 128^3 -> crop 64^3, per-volume displacement and 3-D affine
+    (rotation 15 deg about axis 0, zoom 1.2 about the crop centre), order 3, one edf_deform_grid_batch call."""
+    from elasticdeform_b200 import batch
+    rng = np.random.default_rng(4)
+    th = np.radians(15.0)
+    R = np.array([[1, 0, 0], [0, np.cos(th), -np.sin(th)], [0, np.sin(th), np.cos(th)]]) * 1.2
+    c = np.array([31.5, 31.5, 31.5])
+    A = np.concatenate([R, (c - R @ c)[:, None]], axis=1)
+    Xs = [torch.from_numpy(rng.random((128,) * 3, dtype=np.float32)).to(dev) for _ in range(nb)]
+    Ds = [rng.standard_normal((3, 5, 5, 5)) * 8.0 for _ in range(nb)]
+    crop = (slice(32, 96),) * 3
+    st = torch.cuda.current_stream(dev)
+    out = {}
+    for what in ("fwd", "grad"):
+        ts = []
+        src = Xs
+        if what == "grad":
+            src = [torch.from_numpy(rng.random((64,) * 3, dtype=np.float32)).to(dev) for _ in range(nb)]
+        for r in range(reps + 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); e0.record(st)
+            batch.deform_grid_batch(src, Ds, order=3, crop=crop, prefilter=False, affines=[A] * nb,
+                                    gradient=(what == "grad"), X_shape=(128,) * 3)
+            e1.record(st); torch.cuda.synchronize()
+            if r >= 2: ts.append(e0.elapsed_time(e1))
+        t = float(np.median(ts))
+        out[what] = dict(ms=round(t, 3), Mvox_out_s=round(nb * 64 ** 3 / t / 1e3, 1))
+    print(json.dumps({"config": "cfg4 batch %dx(128^3 -> crop 64^3, affine), order 3, incl. host prep" % nb, **out}), flush=True)
+
+
 def prefilter_times(shape=(256, 256, 256), order=3, reps=5):
     rng = np.random.default_rng(1)
     x = torch.from_numpy(rng.random(shape, dtype=np.float32)).to(dev)
@@ -78,3 +109,4 @@ if __name__ == "__main__":
     run("256^3 f32 order 3 mirror", [S], ['float32'], [3], (5, 5, 5), 8.0, mode='mirror', reps=10)
     run("256^3 f32 order 1 nearest", [S], ['float32'], [1], (5, 5, 5), 8.0, mode='nearest', reps=10)
     prefilter_times()
+    cfg4_batch()
