@@ -21,7 +21,7 @@
 
 struct EdfFastLaunch {
     uint32_t input_mask;           // which p.inp[] entries this launch processes
-    uint32_t pad_;
+    uint32_t rows_per_cta;         // lean kernels: rows of the second-last axis per CTA (multiple of 8, <= 64)
     uint64_t cval_bits[EDF_MAX_INPUTS];   // constant value converted to the output dtype
     int32_t  istr_e[EDF_MAX_INPUTS][EDF_MAX_AXIS];   // element strides (deformed axes)
     int32_t  ostr_e[EDF_MAX_INPUTS][EDF_MAX_AXIS];
@@ -577,12 +577,19 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
         if (done[ii] || cls[ii] == EDF_CLASS_NONE) continue;
         if (cls[ii] == EDF_CLASS_F32 && edf_lean_eligible(p, L, ii)) {
             L.input_mask = 1u << ii;
+            // small volumes: fewer rows per CTA until the grid fills the 148 SMs at least twice over
+            unsigned ry = EDF_FAST_RY;
+            while (ry > EDF_FAST_M &&
+                   (uint64_t)grid.x * ((p.odim[AY] + ry - 1) / ry) * grid.z < 4ull * 148) ry >>= 1;
+            L.rows_per_cta = ry;
+            dim3 lgrid = grid;
+            lgrid.y = (unsigned)((p.odim[AY] + ry - 1) / ry);
             if (p.gradient && edf_gradwin_eligible(p)) {
                 const int rcw = edf_lean_launch_gradwin(p.inp[ii].order, st, p, L, ii);
                 if (rcw < 0) return -1;
                 *name = rcw == 2 ? "lean3d_f32_gradwin_tma" : "lean3d_f32_gradwin";
             } else {
-                edf_lean_launch(p.inp[ii].order, p.gradient, grid, st, p, L, ii);
+                edf_lean_launch(p.inp[ii].order, p.gradient, lgrid, st, p, L, ii);
                 *name = p.gradient ? "lean3d_f32_grad" : "lean3d_f32";
             }
             g_fast_launch_error = cudaGetLastError();

@@ -123,7 +123,8 @@ edf_lean3d_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ E
     constexpr int NT = ORDER + 1;
     constexpr int NCHUNK = EDF_FAST_RY / EDF_FAST_M;
     const int x0 = blockIdx.x * EDF_FAST_TX;
-    const int y0 = blockIdx.y * EDF_FAST_RY;
+    const int ry = (int)L.rows_per_cta;
+    const int y0 = blockIdx.y * ry;
     const int z0 = blockIdx.z * EDF_FAST_G;
     edf_lean_tile_setup(p, s, z0, y0, x0);
 
@@ -137,7 +138,7 @@ edf_lean3d_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ E
 #pragma unroll
     for (int k = 0; k < 4; ++k) wx[k] = s.wx[tx][k];
     const int sxrel = s.sx[tx] - s.sx[0];
-    const int nchunk = min(NCHUNK, (ody - y0 + EDF_FAST_M - 1) / EDF_FAST_M);
+    const int nchunk = min(ry / EDF_FAST_M, (ody - y0 + EDF_FAST_M - 1) / EDF_FAST_M);
     const bool gate = s.nonzero != 0;
     const int nx = s.nx, sy_min = s.sy[0];
     double (*Bw)[EDF_FAST_M][EDF_FAST_NC] = s.Bw[warp];
@@ -343,7 +344,8 @@ edf_lean3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
     constexpr int NT = ORDER + 1;
     constexpr int NCHUNK = EDF_FAST_RY / EDF_FAST_M;
     const int x0 = blockIdx.x * EDF_FAST_TX;
-    const int y0 = blockIdx.y * EDF_FAST_RY;
+    const int ry = (int)L.rows_per_cta;
+    const int y0 = blockIdx.y * ry;
     const int z0 = blockIdx.z * EDF_FAST_G;
     edf_lean_tile_setup(p, s, z0, y0, x0);
 
@@ -357,7 +359,7 @@ edf_lean3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
 #pragma unroll
     for (int k = 0; k < 4; ++k) wx[k] = s.wx[tx][k];
     const int sxrel = s.sx[tx] - s.sx[0];
-    const int nchunk = min(NCHUNK, (ody - y0 + EDF_FAST_M - 1) / EDF_FAST_M);
+    const int nchunk = min(ry / EDF_FAST_M, (ody - y0 + EDF_FAST_M - 1) / EDF_FAST_M);
     const bool gate = s.nonzero != 0;
     const int nx = s.nx, sy_min = s.sy[0];
     double (*Bw)[EDF_FAST_M][EDF_FAST_NC] = s.Bw[warp];
@@ -675,7 +677,8 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
     constexpr int NWIN = EDF_GW_WZ * EDF_GW_WY * EDF_GW_WX;
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * EDF_GW_TX;
-    const int y0 = blockIdx.y * EDF_FAST_RY;
+    const int ry = (int)L.rows_per_cta;
+    const int y0 = blockIdx.y * ry;
     const int z0 = blockIdx.z * EDF_GW_G;
 
     // ---- prologue: control tables, z-contraction A, zeroed window
@@ -731,7 +734,7 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
 #pragma unroll
     for (int k = 0; k < 4; ++k) wx[k] = s.wx[lane][k];
     const int sxrel = s.sx[lane] - s.sx[0];
-    const int nchunk = min(NCHUNK, (ody - y0 + EDF_FAST_M - 1) / EDF_FAST_M);
+    const int nchunk = min(ry / EDF_FAST_M, (ody - y0 + EDF_FAST_M - 1) / EDF_FAST_M);
     const bool gate = s.nonzero != 0;
     const int nx = s.nx, sy_min = s.sy[0];
     double (*Bw)[EDF_GW_MR][EDF_GW_NC] = s.Bw[warp];
@@ -962,12 +965,16 @@ static bool edf_gradwin_eligible(const EdfParams& p)
     return p.naxis == 3 && edf_fast_ctrl_span_ok(p, 2, EDF_GW_TX, EDF_GW_NC) && edf_fast_ctrl_span_ok(p, 1, EDF_FAST_RY, EDF_GW_NC);
 }
 
-static int edf_lean_launch_gradwin(int order, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii)
+static int edf_lean_launch_gradwin(int order, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& Lin, int ii)
 {
     dim3 grid;
     grid.x = (unsigned)((p.odim[2] + EDF_GW_TX - 1) / EDF_GW_TX);
-    grid.y = (unsigned)((p.odim[1] + EDF_FAST_RY - 1) / EDF_FAST_RY);
     grid.z = (unsigned)((p.odim[0] + EDF_GW_G - 1) / EDF_GW_G);
+    unsigned ry = EDF_FAST_RY;                       // fewer rows per CTA for small volumes (fill 148 SMs x 2 CTAs twice)
+    while (ry > EDF_FAST_M && (uint64_t)grid.x * ((p.odim[1] + ry - 1) / ry) * grid.z < 4ull * 148) ry >>= 1;
+    grid.y = (unsigned)((p.odim[1] + ry - 1) / ry);
+    EdfFastLaunch L = Lin;
+    L.rows_per_cta = ry;
     const size_t smem = sizeof(EdfGradWinSmem);
     if (!g_gradwin_configured) {
 #define EDF_GW_ATTR(O)                                                                                           \
