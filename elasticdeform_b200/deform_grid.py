@@ -15,6 +15,7 @@ plug-in) or torch CUDA tensors (zero copies; the result stays on the device).
 PyTorch is used only for device memory, streams and copies.
 """
 import ctypes
+import threading
 import warnings
 
 import numpy
@@ -163,6 +164,216 @@ def _launch(lib, gradient, ins, outs, displacement_f, output_offset, axis, order
     _lib.check(fn(ctypes.byref(pr), _stream_ptr(ins[0].device)))
 
 
+# --------------------------------------------------------------------------------------
+# slab-pipelined host path (NumPy in / NumPy out)
+# --------------------------------------------------------------------------------------
+# A host array has to cross PCIe twice (in and out); for a 256^3 float32 volume that is 2 x 67 MB
+# = ~5 ms against a ~0.7 ms kernel.  PCIe is full duplex, so when the call allows it the volume is
+# cut into slabs along the first array axis and upload, kernel and download of different slabs
+# overlap on three streams.  What makes this legal is a rigorous bound on how far along that axis a
+# voxel can reach: the displacement is a convex combination of the (prefiltered) control-point
+# coefficients (B-spline weights are >= 0 and sum to 1), so |d_0| <= max|coefficient of axis 0|.
+_PIPELINE_MIN_BYTES = 16 << 20
+_PIPELINE_SLABS = 8
+
+
+def _pipeline_plan(Xs, axis, order, mode, prefilter, inverse_affine, in_dim0, out_dim0, gradient):
+    """Slab height along array axis 0, or None when the call has to take the one-shot path."""
+    if inverse_affine is not None:
+        return None
+    if any(_is_tensor(x) for x in Xs):
+        return None
+    for i, x in enumerate(Xs):
+        if len(axis[i]) < 2 or axis[i][0] != 0:            # slabs must be slabs of the first DEFORMED axis
+            return None
+        if prefilter and order[i] > 1:                     # the prefilter recursion needs whole lines
+            return None
+        if int(mode[i]) not in (0, 4):                     # nearest / constant: coordinates are never folded
+            return None                                    # back from far away (wrap, mirror, reflect are)
+        if not x.flags.c_contiguous:
+            return None
+    if max(x.nbytes for x in Xs) < _PIPELINE_MIN_BYTES or min(in_dim0, out_dim0) < 4 * _PIPELINE_SLABS:
+        return None
+    return -(-max(in_dim0, out_dim0) // _PIPELINE_SLABS)
+
+
+def _reach(displacement_f, order):
+    """Upper bound of |source index - (output index + offset)| along axis 0, taps included."""
+    dmax = float(displacement_f[0].abs().max().item())
+    if not numpy.isfinite(dmax):
+        return None
+    return int(numpy.ceil(dmax)) + int(max(order)) + 2
+
+
+def _host_tensor(x):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                       # read-only arrays are only read
+        return torch.from_numpy(x)
+
+
+# Pinned result buffers.  cudaHostAlloc of a 67 MB block costs ~4 ms on the B200 hosts -- more than the
+# kernel and comparable to the PCIe copy -- so result buffers are recycled: the NumPy array handed
+# to the caller is backed by a lease on a pinned block, and when the last array referencing the
+# lease is garbage collected the block goes back to a small pool instead of to cudaFreeHost.
+_POOL_LOCK = threading.Lock()
+_POOL = {}                         # nbytes -> [uint8 pinned tensors]
+_POOL_FREE_BYTES = [0]
+_POOL_MAX_FREE_BYTES = 1 << 30
+_POOL_MAX_PER_SIZE = 4
+
+
+def _pool_release(tensor):
+    n = tensor.numel()
+    with _POOL_LOCK:
+        lst = _POOL.setdefault(n, [])
+        if len(lst) < _POOL_MAX_PER_SIZE and _POOL_FREE_BYTES[0] + n <= _POOL_MAX_FREE_BYTES:
+            lst.append(tensor)
+            _POOL_FREE_BYTES[0] += n
+
+
+class _PinnedLease(object):
+    """Owner of a pinned block as far as NumPy is concerned (arrays built on it keep it alive)."""
+    __slots__ = ("tensor", "__array_interface__", "__weakref__")
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self.__array_interface__ = {"data": (tensor.data_ptr(), False), "shape": (tensor.numel(),),
+                                    "typestr": "|u1", "version": 3}
+
+    def __del__(self):
+        try:
+            _pool_release(self.tensor)
+        except Exception:          # interpreter shutdown
+            pass
+
+
+def _pinned_result(shape, torch_dtype):
+    """(torch view, numpy array) of a recycled pinned block of the given shape / dtype; a plain
+    pageable pair when pinned memory is not available."""
+    shape = tuple(int(v) for v in shape)
+    n = int(numpy.prod(shape, dtype=numpy.int64)) * torch.empty((), dtype=torch_dtype).element_size()
+    if n == 0:
+        t = torch.empty(shape, dtype=torch_dtype)
+        return t, t.numpy()
+    block = None
+    with _POOL_LOCK:
+        lst = _POOL.get(n)
+        if lst:
+            block = lst.pop()
+            _POOL_FREE_BYTES[0] -= n
+    if block is None:
+        try:
+            block = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        except RuntimeError:
+            t = torch.empty(shape, dtype=torch_dtype)
+            return t, t.numpy()
+    lease = _PinnedLease(block)
+    np_dtype = numpy.dtype(str(torch_dtype).replace('torch.', ''))
+    arr = numpy.asarray(lease).view(np_dtype).reshape(shape)
+    return block.view(torch_dtype).view(shape), arr
+
+
+def _pipelined_forward(lib, device, Xs, displacement_f, output_shapes, output_offset, axis, order, mode, cval,
+                       h, flags):
+    n = len(Xs)
+    in0, out0 = Xs[0].shape[0], output_shapes[0][0]
+    off0 = int(output_offset[0]) if output_offset is not None else 0
+    reach = _reach(displacement_f, order)
+    if reach is None:
+        return None
+    cur = torch.cuda.current_stream(device)
+    s_up, s_down = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    X_h = [_host_tensor(x) for x in Xs]
+    X_d = [torch.empty(x.shape, dtype=x.dtype, device=device) for x in X_h]
+    Y_d = [torch.empty(tuple(os), dtype=x.dtype, device=device) for os, x in zip(output_shapes, X_h)]
+    s_up.wait_stream(cur)
+    n_in = -(-in0 // h)
+    up_done = []
+    with torch.cuda.stream(s_up):
+        for j in range(n_in):
+            a, b = j * h, min(in0, (j + 1) * h)
+            for xd, xh in zip(X_d, X_h):
+                xd[a:b].copy_(xh[a:b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s_up)
+            up_done.append(ev)
+    Y_hn = [_pinned_result(os, x.dtype) for os, x in zip(output_shapes, X_h)]   # while the uploads run
+    Y_h = [p[0] for p in Y_hn]
+    for k in range(-(-out0 // h)):
+        a, b = k * h, min(out0, (k + 1) * h)
+        need = min(in0 - 1, max(0, b - 1 + off0 + reach))
+        cur.wait_event(up_done[min(n_in - 1, need // h)])
+        offs = numpy.array([off0 + a] + ([int(v) for v in output_offset[1:]] if output_offset is not None
+                                          else [0] * (len(axis[0]) - 1)), dtype='int64')
+        _launch(lib, 0, X_d, [y[a:b] for y in Y_d], displacement_f, offs, axis, order, mode, cval, None, flags)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        s_down.wait_event(ev)
+        with torch.cuda.stream(s_down):
+            for yh, yd in zip(Y_h, Y_d):
+                yh[a:b].copy_(yd[a:b], non_blocking=True)
+    cur.wait_stream(s_down)
+    cur.wait_stream(s_up)
+    cur.synchronize()
+    return [p[1] for p in Y_hn]
+
+
+def _pipelined_gradient(lib, device, dYs, X_shape, displacement_f, output_offset, axis, order, mode, cval,
+                        h, flags):
+    in0, out0 = X_shape[0][0], dYs[0].shape[0]
+    off0 = int(output_offset[0]) if output_offset is not None else 0
+    reach = _reach(displacement_f, order)
+    if reach is None:
+        return None
+    cur = torch.cuda.current_stream(device)
+    s_up, s_down = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    G_h = [_host_tensor(g) for g in dYs]
+    G_d = [torch.empty(g.shape, dtype=g.dtype, device=device) for g in G_h]
+    dX_d = [torch.zeros(tuple(sh), dtype=g.dtype, device=device) for sh, g in zip(X_shape, G_h)]
+    s_up.wait_stream(cur)
+    n_out = -(-out0 // h)
+    up_done = []
+    with torch.cuda.stream(s_up):
+        for k in range(n_out):
+            a, b = k * h, min(out0, (k + 1) * h)
+            for gd, gh in zip(G_d, G_h):
+                gd[a:b].copy_(gh[a:b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s_up)
+            up_done.append(ev)
+    dX_hn = [_pinned_result(sh, g.dtype) for sh, g in zip(X_shape, G_h)]       # while the uploads run
+    dX_h = [p[0] for p in dX_hn]
+    n_in = -(-in0 // h)
+    flushed = 0                                             # dX slabs [0, flushed) are already on their way home
+
+    def flush_upto(j_end, ev):
+        nonlocal flushed
+        if j_end <= flushed:
+            return
+        s_down.wait_event(ev)
+        with torch.cuda.stream(s_down):
+            a, b = flushed * h, min(in0, j_end * h)
+            for xh, xd in zip(dX_h, dX_d):
+                xh[a:b].copy_(xd[a:b], non_blocking=True)
+        flushed = j_end
+
+    for k in range(n_out):
+        a, b = k * h, min(out0, (k + 1) * h)
+        cur.wait_event(up_done[k])
+        offs = numpy.array([off0 + a] + ([int(v) for v in output_offset[1:]] if output_offset is not None
+                                          else [0] * (len(axis[0]) - 1)), dtype='int64')
+        _launch(lib, 1, dX_d, [g[a:b] for g in G_d], displacement_f, offs, axis, order, mode, cval, None, flags)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        # later output slabs start at b: they cannot reach input planes below b + off0 - reach
+        final_below = n_in if k == n_out - 1 else max(0, (b + off0 - reach) // h)
+        flush_upto(min(n_in, final_below), ev)
+    cur.wait_stream(s_down)
+    cur.wait_stream(s_up)
+    cur.synchronize()
+    return [p[1] for p in dX_hn]
+
+
 def _from_device(t, like):
     """Return the result in the same kind of container as the corresponding input."""
     if _is_tensor(like):
@@ -170,13 +381,10 @@ def _from_device(t, like):
     # NumPy caller: device -> pinned host block from torch's caching host allocator (the block
     # returns to the cache when the caller drops the array), so repeated calls copy at full
     # PCIe speed without a fresh cudaHostAlloc each time.
-    try:
-        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    except RuntimeError:
-        return t.cpu().numpy()
+    host, arr = _pinned_result(t.shape, t.dtype)
     host.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
-    return host.numpy()
+    return arr
 
 
 # --------------------------------------------------------------------------------------
@@ -276,6 +484,17 @@ def deform_grid(X, displacement, order=3, mode='constant', cval=0.0, crop=None, 
     lib = _require_cuda()
     device = _device_of(Xs)
     with torch.cuda.device(device):
+        h = _pipeline_plan(Xs, axis, order, mode, prefilter, inverse_affine,
+                           Xs[0].shape[0], output_shapes[0][0], False)
+        if h is not None:
+            for x in Xs:
+                _lib.dtype_code(x.dtype)
+            displacement_f = _prefilter_displacement(lib, displacement, device)
+            results = _pipelined_forward(lib, device, Xs, displacement_f, output_shapes, output_offset, axis,
+                                         order, mode, cval, h, _flags)
+            if results is not None:
+                return results if isinstance(X, list) else results[0]
+
         Xs_d = [_to_device(x, device) for x in Xs]
 
         # prefilter inputs (ref:155-164): per deformed axis, result rounded to the
@@ -366,6 +585,17 @@ def deform_grid_gradient(dY, displacement, order=3, mode='constant', cval=0.0, c
     lib = _require_cuda()
     device = _device_of(dYs)
     with torch.cuda.device(device):
+        h = _pipeline_plan(dYs, axis, order, mode, prefilter, inverse_affine,
+                           X_shape[0][0] if len(X_shape[0]) else 0, dYs[0].shape[0] if dYs[0].ndim else 0, True)
+        if h is not None:
+            for dy in dYs:
+                _lib.dtype_code(dy.dtype)
+            displacement_f = _prefilter_displacement(lib, displacement, device)
+            results = _pipelined_gradient(lib, device, dYs, [tuple(sh) for sh in X_shape], displacement_f,
+                                          output_offset, axis, order, mode, cval, h, _flags)
+            if results is not None:
+                return results if isinstance(dY, list) else results[0]
+
         dYs_d = [_to_device(dy, device) for dy in dYs]
 
         # initialize gradient outputs (ref:243) -- the scatter accumulates into zeros
