@@ -239,25 +239,30 @@ __device__ __forceinline__ void edf_fast_walk_tile(const EdfParams& p, EdfFastSm
 // ---------------------------------------------------------------------------------------
 // float32 kernel: forward gather (GRAD=false) or gradient scatter (GRAD=true)
 // ---------------------------------------------------------------------------------------
-// all the work for one float32 input at one output voxel (general path: any mode, edges, strides,
-// non-deformed "step" axes)
-template <int NAXIS, int ORDER, bool GRAD>
-__device__ __forceinline__ void edf_fast_f32_one_input(const EdfParams& p, const EdfFastLaunch& L, int ii,
+__device__ __forceinline__ float  edf_fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double edf_fma_t(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ void edf_bits_to(uint64_t bits, float* v) { *v = __uint_as_float((uint32_t)bits); }
+__device__ __forceinline__ void edf_bits_to(uint64_t bits, double* v) { *v = __longlong_as_double((long long)bits); }
+
+// all the work for one float32 / float64 input at one output voxel (general path: any mode, edges,
+// strides, non-deformed "step" axes); weights and accumulation in the array's own precision
+template <int NAXIS, int ORDER, bool GRAD, typename T>
+__device__ __forceinline__ void edf_fast_real_one_input(const EdfParams& p, const EdfFastLaunch& L, int ii,
                                                        const int* o, const double* in)
 {
     constexpr int NT = ORDER + 1;
     const EdfInputDesc& d = p.inp[ii];
     bool constant = false, edge = false;
-    float w[NAXIS][NT];
+    T w[NAXIS][NT];
     int off[NAXIS][NT];
 #pragma unroll
     for (int h = 0; h < NAXIS; ++h) {
         int st = 0;
-        float fr = 0.f;
+        T fr = (T)0;
         if (!constant && !edf_fast_finish(p, d.mode, ORDER, h, in[h], &st, &fr)) constant = true;
         if (!constant) {
             edge |= edf_fast_tap_offsets<ORDER>(st, (int)p.idim[h], L.istr_e[ii][h], off[h]);
-            if (ORDER > 0) edf_bspline_weights_f32<ORDER>(fr, w[h]);
+            if (ORDER > 0) edf_bspline_weights_t<ORDER, T>(fr, w[h]);
         }
     }
     int64_t obase = 0;
@@ -282,12 +287,12 @@ __device__ __forceinline__ void edf_fast_f32_one_input(const EdfParams& p, const
                 ostep += d.out_step_str[q] * c;
             }
         }
-        float* po = (float*)(d.out + ostep) + obase;
+        T* po = (T*)(d.out + ostep) + obase;
         if (!GRAD) {
-            const float* __restrict__ pi = (const float*)(d.in + istep);
-            float t;
+            const T* __restrict__ pi = (const T*)(d.in + istep);
+            T t;
             if (constant) {
-                t = __uint_as_float((uint32_t)L.cval_bits[ii]);
+                edf_bits_to(L.cval_bits[ii], &t);
             } else if (ORDER == 0) {
                 int e = 0;
 #pragma unroll
@@ -297,63 +302,63 @@ __device__ __forceinline__ void edf_fast_f32_one_input(const EdfParams& p, const
                 int e0 = 0;
 #pragma unroll
                 for (int h = 0; h < NAXIS; ++h) e0 += off[h][0];
-                const float* base = pi + e0;
-                t = 0.f;
+                const T* base = pi + e0;
+                t = (T)0;
                 if (NAXIS == 3) {
 #pragma unroll
                     for (int i = 0; i < NT; ++i) {
-                        const float* pz = base + (int64_t)i * sz_e;
-                        float ti = 0.f;
+                        const T* pz = base + (int64_t)i * sz_e;
+                        T ti = (T)0;
 #pragma unroll
                         for (int j = 0; j < NT; ++j) {
-                            const float* row = pz + (int64_t)j * sy_e;
-                            float tj = 0.f;
+                            const T* row = pz + (int64_t)j * sy_e;
+                            T tj = (T)0;
 #pragma unroll
-                            for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + k), w[2][k], tj);
-                            ti = fmaf(tj, w[1][j], ti);
+                            for (int k = 0; k < NT; ++k) tj = edf_fma_t(__ldg(row + k), w[2][k], tj);
+                            ti = edf_fma_t(tj, w[1][j], ti);
                         }
-                        t = fmaf(ti, w[0][i], t);
+                        t = edf_fma_t(ti, w[0][i], t);
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
-                        const float* row = base + (int64_t)j * sz_e;
-                        float tj = 0.f;
+                        const T* row = base + (int64_t)j * sz_e;
+                        T tj = (T)0;
 #pragma unroll
-                        for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + k), w[1][k], tj);
-                        t = fmaf(tj, w[0][j], t);
+                        for (int k = 0; k < NT; ++k) tj = edf_fma_t(__ldg(row + k), w[1][k], tj);
+                        t = edf_fma_t(tj, w[0][j], t);
                     }
                 }
             } else if (NAXIS == 3) {
-                t = 0.f;
+                t = (T)0;
 #pragma unroll
                 for (int i = 0; i < NT; ++i) {
-                    float ti = 0.f;
+                    T ti = (T)0;
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
-                        const float* row = pi + (off[0][i] + off[1][j]);
-                        float tj = 0.f;
+                        const T* row = pi + (off[0][i] + off[1][j]);
+                        T tj = (T)0;
 #pragma unroll
-                        for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + off[2][k]), w[2][k], tj);
-                        ti = fmaf(tj, w[1][j], ti);
+                        for (int k = 0; k < NT; ++k) tj = edf_fma_t(__ldg(row + off[2][k]), w[2][k], tj);
+                        ti = edf_fma_t(tj, w[1][j], ti);
                     }
-                    t = fmaf(ti, w[0][i], t);
+                    t = edf_fma_t(ti, w[0][i], t);
                 }
             } else {
-                t = 0.f;
+                t = (T)0;
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
-                    const float* row = pi + off[0][j];
-                    float tj = 0.f;
+                    const T* row = pi + off[0][j];
+                    T tj = (T)0;
 #pragma unroll
-                    for (int k = 0; k < NT; ++k) tj = fmaf(__ldg(row + off[1][k]), w[1][k], tj);
-                    t = fmaf(tj, w[0][j], t);
+                    for (int k = 0; k < NT; ++k) tj = edf_fma_t(__ldg(row + off[1][k]), w[1][k], tj);
+                    t = edf_fma_t(tj, w[0][j], t);
                 }
             }
             *po = t;
         } else if (!constant) {
-            float* pi = (float*)(d.in + istep);
-            const float gval = *po;
+            T* pi = (T*)(d.in + istep);
+            const T gval = *po;
             if (ORDER == 0) {
                 int e = 0;
 #pragma unroll
@@ -362,11 +367,11 @@ __device__ __forceinline__ void edf_fast_f32_one_input(const EdfParams& p, const
             } else if (NAXIS == 3) {
 #pragma unroll
                 for (int i = 0; i < NT; ++i) {
-                    const float gi = gval * w[0][i];
+                    const T gi = gval * w[0][i];
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
-                        const float gj = gi * w[1][j];
-                        float* row = pi + (off[0][i] + off[1][j]);
+                        const T gj = gi * w[1][j];
+                        T* row = pi + (off[0][i] + off[1][j]);
 #pragma unroll
                         for (int k = 0; k < NT; ++k) atomicAdd(row + off[2][k], gj * w[2][k]);
                     }
@@ -374,8 +379,8 @@ __device__ __forceinline__ void edf_fast_f32_one_input(const EdfParams& p, const
             } else {
 #pragma unroll
                 for (int j = 0; j < NT; ++j) {
-                    const float gj = gval * w[0][j];
-                    float* row = pi + off[0][j];
+                    const T gj = gval * w[0][j];
+                    T* row = pi + off[0][j];
 #pragma unroll
                     for (int k = 0; k < NT; ++k) atomicAdd(row + off[1][k], gj * w[1][k]);
                 }
@@ -385,7 +390,14 @@ __device__ __forceinline__ void edf_fast_f32_one_input(const EdfParams& p, const
 }
 
 template <int NAXIS, int ORDER, bool GRAD>
-struct EdfFastF32Body {
+__device__ __forceinline__ void edf_fast_f32_one_input(const EdfParams& p, const EdfFastLaunch& L, int ii,
+                                                       const int* o, const double* in)
+{
+    edf_fast_real_one_input<NAXIS, ORDER, GRAD, float>(p, L, ii, o, in);
+}
+
+template <int NAXIS, int ORDER, bool GRAD, typename T>
+struct EdfFastRealBody {
     const EdfParams& p;
     const EdfFastLaunch& L;
 
@@ -393,17 +405,17 @@ struct EdfFastF32Body {
     {
         for (int ii = 0; ii < p.ninputs; ++ii) {
             if (!((L.input_mask >> ii) & 1u)) continue;
-            edf_fast_f32_one_input<NAXIS, ORDER, GRAD>(p, L, ii, o, in);
+            edf_fast_real_one_input<NAXIS, ORDER, GRAD, T>(p, L, ii, o, in);
         }
     }
 };
 
-template <int NAXIS, int ORDER, bool GRAD>
+template <int NAXIS, int ORDER, bool GRAD, typename T>
 __global__ void __launch_bounds__(EDF_FAST_THREADS, 2)
-edf_fast_f32_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L)
+edf_fast_real_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L)
 {
     __shared__ EdfFastSmem<NAXIS> s;
-    EdfFastF32Body<NAXIS, ORDER, GRAD> body{p, L};
+    EdfFastRealBody<NAXIS, ORDER, GRAD, T> body{p, L};
     edf_fast_walk_tile<NAXIS>(p, s, body);
 }
 
@@ -467,7 +479,7 @@ edf_fast_copy_kernel(const __grid_constant__ EdfParams p, const __grid_constant_
 // ---------------------------------------------------------------------------------------
 static thread_local cudaError_t g_fast_launch_error = cudaSuccess;
 
-enum { EDF_CLASS_NONE = 0, EDF_CLASS_F32 = 1, EDF_CLASS_COPY = 2 };
+enum { EDF_CLASS_NONE = 0, EDF_CLASS_F32 = 1, EDF_CLASS_COPY = 2, EDF_CLASS_F64 = 3 };
 
 static inline int edf_elem_size(int dt)
 {
@@ -487,6 +499,7 @@ static int edf_fast_input_class(const EdfParams& p, int ii, EdfFastLaunch& L)
     const int es = edf_elem_size(d.in_dtype);
     int cls;
     if (d.in_dtype == EDF_F32) cls = EDF_CLASS_F32;
+    else if (d.in_dtype == EDF_F64) cls = EDF_CLASS_F64;
     else if (d.order == 0 && !p.gradient && d.in_dtype != EDF_BOOL) cls = EDF_CLASS_COPY;
     else return EDF_CLASS_NONE;
     int64_t max_in = 0, max_out = 0;
@@ -510,17 +523,17 @@ static int edf_fast_input_class(const EdfParams& p, int ii, EdfFastLaunch& L)
     return cls;
 }
 
-template <int NAXIS, bool GRAD>
-static void edf_fast_launch_f32(int order, dim3 grid, cudaStream_t st, const EdfParams& p,
-                                const EdfFastLaunch& L)
+template <int NAXIS, bool GRAD, typename T>
+static void edf_fast_launch_real(int order, dim3 grid, cudaStream_t st, const EdfParams& p,
+                                 const EdfFastLaunch& L)
 {
     switch (order) {
-    case 0: edf_fast_f32_kernel<NAXIS, 0, GRAD><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
-    case 1: edf_fast_f32_kernel<NAXIS, 1, GRAD><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
-    case 2: edf_fast_f32_kernel<NAXIS, 2, GRAD><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
-    case 3: edf_fast_f32_kernel<NAXIS, 3, GRAD><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
-    case 4: edf_fast_f32_kernel<NAXIS, 4, GRAD><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
-    default: edf_fast_f32_kernel<NAXIS, 5, GRAD><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    case 0: edf_fast_real_kernel<NAXIS, 0, GRAD, T><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    case 1: edf_fast_real_kernel<NAXIS, 1, GRAD, T><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    case 2: edf_fast_real_kernel<NAXIS, 2, GRAD, T><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    case 3: edf_fast_real_kernel<NAXIS, 3, GRAD, T><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    case 4: edf_fast_real_kernel<NAXIS, 4, GRAD, T><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
+    default: edf_fast_real_kernel<NAXIS, 5, GRAD, T><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L); break;
     }
 }
 
@@ -613,13 +626,23 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
         if (cls[ii] == EDF_CLASS_F32) {
             const int order = p.inp[ii].order;
             if (p.naxis == 3) {
-                if (p.gradient) edf_fast_launch_f32<3, true>(order, grid, st, p, L);
-                else            edf_fast_launch_f32<3, false>(order, grid, st, p, L);
+                if (p.gradient) edf_fast_launch_real<3, true, float>(order, grid, st, p, L);
+                else            edf_fast_launch_real<3, false, float>(order, grid, st, p, L);
             } else {
-                if (p.gradient) edf_fast_launch_f32<2, true>(order, grid, st, p, L);
-                else            edf_fast_launch_f32<2, false>(order, grid, st, p, L);
+                if (p.gradient) edf_fast_launch_real<2, true, float>(order, grid, st, p, L);
+                else            edf_fast_launch_real<2, false, float>(order, grid, st, p, L);
             }
             *name = p.gradient ? "fast_f32_grad" : "fast_f32";
+        } else if (cls[ii] == EDF_CLASS_F64) {
+            const int order = p.inp[ii].order;
+            if (p.naxis == 3) {
+                if (p.gradient) edf_fast_launch_real<3, true, double>(order, grid, st, p, L);
+                else            edf_fast_launch_real<3, false, double>(order, grid, st, p, L);
+            } else {
+                if (p.gradient) edf_fast_launch_real<2, true, double>(order, grid, st, p, L);
+                else            edf_fast_launch_real<2, false, double>(order, grid, st, p, L);
+            }
+            *name = p.gradient ? "fast_f64_grad" : "fast_f64";
         } else {
             if (p.naxis == 3) edf_fast_launch_copy<3>(es, grid, st, p, L);
             else              edf_fast_launch_copy<2>(es, grid, st, p, L);

@@ -57,8 +57,9 @@ EDF_HD bool edf_fast_ctrl_span_ok(const EdfParams& p, int a, int T, int NC = EDF
 
 // Finish one axis for one input: boundary map, window start, fractional offset.
 // Returns false when the voxel takes the constant value (deform.c:782, :819-823).
+template <typename F>
 EDF_HD bool edf_fast_finish(const EdfParams& p, int mode, int order, int h, double in,
-                            int* start, float* frac)
+                            int* start, F* frac)
 {
     double cc = in;
     if (!(in >= 0.0 && in <= p.idim_m1[h])) {               // same map as edf_map_coordinate
@@ -68,54 +69,60 @@ EDF_HD bool edf_fast_finish(const EdfParams& p, int mode, int order, int h, doub
     if (!(cc > -1.0)) return false;
     const double fl = (order & 1) ? floor(cc) : floor(xadd(cc, 0.5));
     *start = (int)fl - order / 2;
-    *frac = (float)(cc - fl);
+    *frac = (F)(cc - fl);
     return true;
 }
 
 // B-spline basis weights in float from the fractional offset x (= delta to the middle
 // knot, as produced by edf_fast_finish).  Same closed forms as deform.c:171-265.
-template <int ORDER>
-EDF_HD void edf_bspline_weights_f32(float x, float* w)
+template <int ORDER, typename F>
+EDF_HD void edf_bspline_weights_t(F x, F* w)
 {
-    const float y = x, z = 1.0f - x;
+    const F y = x, z = (F)1.0 - x;
     if (ORDER == 1) {
-        w[0] = 1.0f - x;
+        w[0] = (F)1.0 - x;
     } else if (ORDER == 2) {
-        w[1] = 0.75f - x * x;
-        const float yy = 0.5f - x;
-        w[0] = 0.5f * yy * yy;
+        w[1] = (F)0.75 - x * x;
+        const F yy = (F)0.5 - x;
+        w[0] = (F)0.5 * yy * yy;
     } else if (ORDER == 3) {
-        w[1] = (y * y * (y - 2.0f) * 3.0f + 4.0f) * (1.0f / 6.0f);
-        w[2] = (z * z * (z - 2.0f) * 3.0f + 4.0f) * (1.0f / 6.0f);
-        w[0] = z * z * z * (1.0f / 6.0f);
+        w[1] = (y * y * (y - (F)2.0) * (F)3.0 + (F)4.0) * ((F)1.0 / (F)6.0);
+        w[2] = (z * z * (z - (F)2.0) * (F)3.0 + (F)4.0) * ((F)1.0 / (F)6.0);
+        w[0] = z * z * z * ((F)1.0 / (F)6.0);
     } else if (ORDER == 4) {
-        float t = x * x;
-        w[2] = t * (t * 0.25f - 0.625f) + 115.0f / 192.0f;
-        float yy = 1.0f + x;
-        w[1] = yy * (yy * (yy * (5.0f - yy) * (1.0f / 6.0f) - 1.25f) + 5.0f / 24.0f) + 55.0f / 96.0f;
-        w[3] = z * (z * (z * (5.0f - z) * (1.0f / 6.0f) - 1.25f) + 5.0f / 24.0f) + 55.0f / 96.0f;
-        yy = 0.5f - x;
+        F t = x * x;
+        w[2] = t * (t * (F)0.25 - (F)0.625) + (F)115.0 / (F)192.0;
+        F yy = (F)1.0 + x;
+        w[1] = yy * (yy * (yy * ((F)5.0 - yy) * ((F)1.0 / (F)6.0) - (F)1.25) + (F)5.0 / (F)24.0) + (F)55.0 / (F)96.0;
+        w[3] = z * (z * (z * ((F)5.0 - z) * ((F)1.0 / (F)6.0) - (F)1.25) + (F)5.0 / (F)24.0) + (F)55.0 / (F)96.0;
+        yy = (F)0.5 - x;
         t = yy * yy;
-        w[0] = t * t * (1.0f / 24.0f);
+        w[0] = t * t * ((F)1.0 / (F)24.0);
     } else if (ORDER == 5) {
-        float t = y * y;
-        w[2] = t * (t * (0.25f - y * (1.0f / 12.0f)) - 0.5f) + 0.55f;
+        F t = y * y;
+        w[2] = t * (t * ((F)0.25 - y * ((F)1.0 / (F)12.0)) - (F)0.5) + (F)0.55;
         t = z * z;
-        w[3] = t * (t * (0.25f - z * (1.0f / 12.0f)) - 0.5f) + 0.55f;
-        float yy = y + 1.0f;
-        w[1] = yy * (yy * (yy * (yy * (yy * (1.0f / 24.0f) - 0.375f) + 1.25f) - 1.75f) + 0.625f) + 0.425f;
-        float zz = z + 1.0f;
-        w[4] = zz * (zz * (zz * (zz * (zz * (1.0f / 24.0f) - 0.375f) + 1.25f) - 1.75f) + 0.625f) + 0.425f;
-        yy = 1.0f - x;
+        w[3] = t * (t * ((F)0.25 - z * ((F)1.0 / (F)12.0)) - (F)0.5) + (F)0.55;
+        F yy = y + (F)1.0;
+        w[1] = yy * (yy * (yy * (yy * (yy * ((F)1.0 / (F)24.0) - (F)0.375) + (F)1.25) - (F)1.75) + (F)0.625) + (F)0.425;
+        F zz = z + (F)1.0;
+        w[4] = zz * (zz * (zz * (zz * (zz * ((F)1.0 / (F)24.0) - (F)0.375) + (F)1.25) - (F)1.75) + (F)0.625) + (F)0.425;
+        yy = (F)1.0 - x;
         t = yy * yy;
-        w[0] = yy * t * t * (1.0f / 120.0f);
+        w[0] = yy * t * t * ((F)1.0 / (F)120.0);
     }
     if (ORDER >= 1) {
-        float last = 1.0f;
+        F last = (F)1.0;
 #pragma unroll
         for (int i = 0; i < ORDER; ++i) last -= w[i];
         w[ORDER] = last;
     }
+}
+
+template <int ORDER>
+EDF_HD void edf_bspline_weights_f32(float x, float* w)
+{
+    edf_bspline_weights_t<ORDER, float>(x, w);
 }
 
 // ---------------------------------------------------------------------------------------
