@@ -115,8 +115,8 @@ __device__ __forceinline__ bool edf_lean_axis(const EdfParams& p, int h, int mod
     return false;
 }
 
-template <int ORDER, bool GRAD, int MINB = 2>
-__global__ void __launch_bounds__(EDF_FAST_THREADS, MINB)
+template <int ORDER, bool GRAD>
+__global__ void __launch_bounds__(EDF_FAST_THREADS, 2)
 edf_lean3d_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii)
 {
     __shared__ EdfLeanSmem s;
@@ -566,9 +566,7 @@ static bool edf_lean_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii
 static void edf_lean_launch(int order, int gradient, dim3 grid, cudaStream_t st, const EdfParams& p,
                             const EdfFastLaunch& L, int ii)
 {
-    static int variant = -1;                  // experiment knob: 1 = one voxel at a time (previous forward kernel)
-    if (variant < 0) { const char* e = getenv("EDF_LEAN_VARIANT"); variant = e ? atoi(e) : 0; }
-    if (!gradient && variant != 1) {
+    if (!gradient) {                                  // batched forward kernel
         switch (order) {
         case 0: edf_lean3d_fwd_kernel<0, 4><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
         case 1: edf_lean3d_fwd_kernel<1, 4><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
@@ -579,19 +577,14 @@ static void edf_lean_launch(int order, int gradient, dim3 grid, cudaStream_t st,
         }
         return;
     }
-#define EDF_LEAN_CASE(O)                                                                       \
-    case O:                                                                                    \
-        if (gradient) edf_lean3d_kernel<O, true><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii);  \
-        else          edf_lean3d_kernel<O, false><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); \
-        break;
-    switch (order) {
-        EDF_LEAN_CASE(0) EDF_LEAN_CASE(1) EDF_LEAN_CASE(2) EDF_LEAN_CASE(3) EDF_LEAN_CASE(4)
-    default:
-        if (gradient) edf_lean3d_kernel<5, true><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii);
-        else          edf_lean3d_kernel<5, false><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii);
-        break;
+    switch (order) {                                  // plain scatter (no accumulation window)
+    case 0: edf_lean3d_kernel<0, true><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
+    case 1: edf_lean3d_kernel<1, true><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
+    case 2: edf_lean3d_kernel<2, true><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
+    case 3: edf_lean3d_kernel<3, true><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
+    case 4: edf_lean3d_kernel<4, true><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
+    default: edf_lean3d_kernel<5, true><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
     }
-#undef EDF_LEAN_CASE
 }
 
 // =======================================================================================
@@ -659,6 +652,23 @@ __device__ __forceinline__ void edf_gw_coords(const EdfParams& p, const double (
         iny = edf_source_coordinate<3, int>(p, o, 1, dy);
         inx = edf_source_coordinate<3, int>(p, o, 2, dx);
     }
+}
+
+// rare voxel of the window gradient (next to a rounding / boundary threshold): reference-order
+// re-evaluation, then the general scatter with global atomics
+template <int ORDER>
+__device__ __noinline__ void edf_gradwin_slow_voxel(const EdfParams& p, const EdfFastLaunch& L, int ii,
+                                                    int z, int y, int x, double inz, double iny, double inx, bool gate)
+{
+    int o[3] = {z, y, x};
+    double in[3] = {inz, iny, inx};
+    if (gate && (edf_near_half_integer(in[0]) || edf_near_half_integer(in[1]) || edf_near_half_integer(in[2]))) {
+        double dd[3];
+        edf_displacement_exact_cold<3>(p, o, dd);
+#pragma unroll
+        for (int h = 0; h < 3; ++h) in[h] = edf_source_coordinate<3, int>(p, o, h, dd[h]);
+    }
+    edf_fast_f32_one_input<3, ORDER, true>(p, L, ii, o, in);
 }
 
 // FLUSH: 0 = scalar atomics, 1 = 16-byte vector atomics, 2 = TMA bulk reduce-add per window row
@@ -811,7 +821,124 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
             const int wz0 = s.wmin[0] - (ORDER + 1) / 2 - EDF_GW_MARGIN;
             const int wy0 = s.wmin[1] - (ORDER + 1) / 2 - EDF_GW_MARGIN;
             const int wx0 = (s.wmin[2] - (ORDER + 1) / 2 - EDF_GW_MARGIN) & ~3;   // 16-byte aligned columns
-            if (tok) {
+            if (tok && ORDER <= 1) {
+                // rows of this warp, U at a time: branch-free coordinates / classification for all U, then the
+                // scatters.  Rare voxels (next to a threshold) go out of line; voxels at the volume border or
+                // outside the window use direct global atomics.
+                constexpr int U = 4;      // orders 0/1 only: at order 3 the batched form spills (0.92 vs 0.87 ms)
+                const bool cmode = mode == EDF_MODE_CONSTANT;
+#pragma unroll 1
+                for (int m0 = 0; m0 <= mrlast; m0 += U) {
+                    double inz[U], iny[U], inx[U];
+                    int stz[U], sty[U], stx[U];
+                    float fz[U], fy[U], fx[U], gv[U];
+                    bool act[U], slow[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int m = min(m0 + u, mrlast);
+                        const int y = yc0 + mr0 + m;
+                        const bool valid = (m0 + u) <= mrlast;
+                        gv[u] = valid ? __ldg(pdy + (obase_zx + (int64_t)y * osy)) : 0.f;   // L1 hit (read above)
+                        edf_gw_coords(p, Bw, m, sxrel, wx, affine, z, y, x, bz, bx, offy, inz[u], iny[u], inx[u]);
+                        double cz = fmin(fmax(inz[u], 0.0), limz);
+                        double cy = fmin(fmax(iny[u], 0.0), limy);
+                        double cx = fmin(fmax(inx[u], 0.0), limx);
+                        const bool inr = (cz == inz[u]) & (cy == iny[u]) & (cx == inx[u]);
+                        bool mapped_danger = false, nanflag = false;
+                        if (!cmode && !inr) {
+                            if (cz != inz[u]) { mapped_danger |= edf_near_half_integer(inz[u]); cz = edf_map_coordinate_cold(inz[u], lenz, mode); }
+                            if (cy != iny[u]) { mapped_danger |= edf_near_half_integer(iny[u]); cy = edf_map_coordinate_cold(iny[u], leny, mode); }
+                            if (cx != inx[u]) { mapped_danger |= edf_near_half_integer(inx[u]); cx = edf_map_coordinate_cold(inx[u], lenx, mode); }
+                            if (!((cz > -1.0) & (cy > -1.0) & (cx > -1.0))) { nanflag = true; cz = cy = cx = 0.0; }
+                        }
+                        const double flz = (ORDER & 1) ? floor(cz) : floor(xadd(cz, 0.5));
+                        const double fly = (ORDER & 1) ? floor(cy) : floor(xadd(cy, 0.5));
+                        const double flx = (ORDER & 1) ? floor(cx) : floor(xadd(cx, 0.5));
+                        fz[u] = (float)xsub(cz, flz);
+                        fy[u] = (float)xsub(cy, fly);
+                        fx[u] = (float)xsub(cx, flx);
+                        stz[u] = (int)flz - ORDER / 2;
+                        sty[u] = (int)fly - ORDER / 2;
+                        stx[u] = (int)flx - ORDER / 2;
+                        bool danger;
+                        if (ORDER & 1)
+                            danger = (fz[u] < EDF_LEAN_EPSF) | (fz[u] > 1.0f - EDF_LEAN_EPSF) | (fy[u] < EDF_LEAN_EPSF) |
+                                     (fy[u] > 1.0f - EDF_LEAN_EPSF) | (fx[u] < EDF_LEAN_EPSF) | (fx[u] > 1.0f - EDF_LEAN_EPSF);
+                        else
+                            danger = (fabsf(fz[u]) < EDF_LEAN_EPSF) | (fabsf(fz[u]) > 0.5f - EDF_LEAN_EPSF) |
+                                     (fabsf(fy[u]) < EDF_LEAN_EPSF) | (fabsf(fy[u]) > 0.5f - EDF_LEAN_EPSF) |
+                                     (fabsf(fx[u]) < EDF_LEAN_EPSF) | (fabsf(fx[u]) > 0.5f - EDF_LEAN_EPSF);
+                        danger |= mapped_danger;
+                        bool nearmiss = false;
+                        if (cmode) {
+                            const double qz = fabs(xsub(inz[u], cz)), qy = fabs(xsub(iny[u], cy)), qx = fabs(xsub(inx[u], cx));
+                            nearmiss = ((qz > 0.0) & (qz < EDF_FAST_EPS)) | ((qy > 0.0) & (qy < EDF_FAST_EPS)) |
+                                       ((qx > 0.0) & (qx < EDF_FAST_EPS));
+                        }
+                        const bool live = valid & (gv[u] != 0.f);
+                        slow[u] = live & ((gate & ((inr | !cmode) ? danger : nearmiss)) | nanflag);
+                        act[u] = live & !slow[u] & (inr | !cmode);          // constant voxels pass no gradient (deform.c:928)
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (!act[u]) continue;
+                        float wzf[NT], wyf[NT], wxf[NT];
+                        if (ORDER > 0) {
+                            edf_bspline_weights_f32<ORDER>(fz[u], wzf);
+                            edf_bspline_weights_f32<ORDER>(fy[u], wyf);
+                            edf_bspline_weights_f32<ORDER>(fx[u], wxf);
+                        }
+                        const bool edge = (stz[u] < 0) | (stz[u] + ORDER >= lenz) | (sty[u] < 0) | (sty[u] + ORDER >= leny) |
+                                          (stx[u] < 0) | (stx[u] + ORDER >= lenx);
+                        const int rz = stz[u] - wz0, ry_ = sty[u] - wy0, rx = stx[u] - wx0;
+                        const bool inwin = (rz >= 0) & (rz + ORDER < EDF_GW_WZ) & (ry_ >= 0) & (ry_ + ORDER < EDF_GW_WY) &
+                                           (rx >= 0) & (rx + ORDER < EDF_GW_WX);
+                        if (!edge && inwin) {
+                            int* wbase = s.win + ((rz * EDF_GW_WY + ry_) * EDF_GW_WX + rx);
+                            const float gs = gv[u] * scale;
+#pragma unroll
+                            for (int i = 0; i < NT; ++i) {
+                                const float gi = (ORDER > 0) ? gs * wzf[i] : gs;
+#pragma unroll
+                                for (int j = 0; j < NT; ++j) {
+                                    const float gj = (ORDER > 0) ? gi * wyf[j] : gi;
+                                    int* r = wbase + (i * EDF_GW_WY + j) * EDF_GW_WX;
+#pragma unroll
+                                    for (int k = 0; k < NT; ++k)
+                                        atomicAdd(r + k, __float2int_rn((ORDER > 0) ? gj * wxf[k] : gj));
+                                }
+                            }
+                        } else {
+                            // border of the volume / outside the accumulation window: direct global atomics
+                            int ozt[NT], oyt[NT], oxt[NT];
+#pragma unroll
+                            for (int i = 0; i < NT; ++i) {
+                                ozt[i] = edf_mirror_index32(stz[u] + i, lenz) * isz;
+                                oyt[i] = edf_mirror_index32(sty[u] + i, leny) * isy;
+                                oxt[i] = edf_mirror_index32(stx[u] + i, lenx);
+                            }
+#pragma unroll
+                            for (int i = 0; i < NT; ++i) {
+                                const float gi = (ORDER > 0) ? gv[u] * wzf[i] : gv[u];
+#pragma unroll
+                                for (int j = 0; j < NT; ++j) {
+                                    const float gj = (ORDER > 0) ? gi * wyf[j] : gi;
+                                    float* r = pdx + (ozt[i] + oyt[j]);
+#pragma unroll
+                                    for (int k = 0; k < NT; ++k)
+                                        atomicAdd(r + oxt[k], (ORDER > 0) ? gj * wxf[k] : gj);
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (slow[u])
+                            edf_gradwin_slow_voxel<ORDER>(p, L, ii, z, yc0 + mr0 + m0 + u, x, inz[u], iny[u], inx[u], gate);
+                }
+            }
+            if (tok && ORDER >= 2) {
+                // one voxel at a time (64+ taps keep the registers full)
 #pragma unroll 1
                 for (int m = 0; m <= mrlast; ++m) {
                     const int y = yc0 + mr0 + m;
