@@ -75,7 +75,8 @@ _lib_lock = threading.Lock()
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libedf_b200.so")
+    # EDF_B200_LIB: another build of the same library (kernel A/B experiments, scripts/ab_variants.sh)
+    return os.environ.get("EDF_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libedf_b200.so")
 
 
 def load_library():

@@ -46,8 +46,14 @@ def needs_build():
     return any(os.path.getmtime(s) > t for s in _sources() if os.path.exists(s))
 
 
-def build_library(force=False, verbose=False, extra_flags=()):
-    """Compile csrc/edf_api.cu -> libedf_b200.so. Returns the library path."""
+def build_library(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile csrc/edf_api.cu -> libedf_b200.so (or ``out``). Returns the library path."""
+    if out is not None:
+        cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, "-o", out, os.path.join(CSRC, "edf_api.cu")]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+        return out
     if not force and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
@@ -63,6 +69,9 @@ def build_library(force=False, verbose=False, extra_flags=()):
 
 
 if __name__ == "__main__":
-    p = build_library(force="--force" in sys.argv, verbose=True,
-                      extra_flags=(["-Xptxas", "-v"] if "--ptxas" in sys.argv else []))
+    # python -m elasticdeform_b200.build [--force] [--ptxas] [--out PATH] [-DNAME=VALUE ...]
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    p = build_library(force="--force" in sys.argv, verbose=True, out=out,
+                      extra_flags=(["-Xptxas", "-v"] if "--ptxas" in sys.argv else []) + defs)
     print("built", p)

@@ -336,8 +336,14 @@ __device__ __forceinline__ int edf_mirror1(int idx, int len)
     return idx >= len ? 2 * len - 2 - idx : idx;
 }
 
+#ifndef EDF_LEAN_FWD_MINB
+#define EDF_LEAN_FWD_MINB 2        // CTAs per SM the batched forward kernel is compiled for
+#endif
+#ifndef EDF_LEAN_FWD_U3
+#define EDF_LEAN_FWD_U3 2          // rows per iteration at orders 2 and 3
+#endif
 template <int ORDER, int U>
-__global__ void __launch_bounds__(EDF_FAST_THREADS, 2)
+__global__ void __launch_bounds__(EDF_FAST_THREADS, EDF_LEAN_FWD_MINB)
 edf_lean3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii)
 {
     __shared__ EdfLeanSmem s;
@@ -380,16 +386,24 @@ edf_lean3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
     const double offy = p.ooff_d[1];
 
     for (int c = 0; c < nchunk; ++c) {
-        for (int e = lane; e < 3 * EDF_FAST_M * nx; e += 32) {
-            const int jx = e % nx;
-            const int m = (e / nx) % EDF_FAST_M;
-            const int h = e / (nx * EDF_FAST_M);
+        {
+            // lane -> (row m, column phase q): no integer division in the table loop
+            static_assert(EDF_FAST_M == 8, "lane mapping of the B table assumes 8 rows per chunk");
+            const int m = lane & 7, q = lane >> 3;
             const int row = c * EDF_FAST_M + m;
             const int r0 = s.sy[row] - sy_min;
-            double b = 0.0;
+            double wyr[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b = fma(s.A[h][g][r0 + j][jx], s.wy[row][j], b);
-            Bw[h][m][jx] = b;
+            for (int j = 0; j < 4; ++j) wyr[j] = s.wy[row][j];
+            // the 3 * nx (component, column) pairs go round the 4 phases; nx >= 4, so one wrap per step
+            for (int h = 0, jx = q; h < 3;) {
+                double b = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b = fma(s.A[h][g][r0 + j][jx], wyr[j], b);
+                Bw[h][m][jx] = b;
+                jx += 4;
+                if (jx >= nx) { jx -= nx; ++h; }
+            }
         }
         __syncwarp();
         if (tok) {
@@ -426,17 +440,21 @@ edf_lean3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
                         inx[u] = edf_source_coordinate<3, int>(p, o, 2, dx);
                     }
                     // clamp into the volume: out-of-range voxels get a harmless in-range address
-                    double cz = fmin(fmax(inz[u], 0.0), limz);
-                    double cy = fmin(fmax(iny[u], 0.0), limy);
-                    double cx = fmin(fmax(inx[u], 0.0), limx);
-                    const bool inr = (cz == inz[u]) & (cy == iny[u]) & (cx == inx[u]);   // false for NaN too
+                    // (comparisons + selects: fmin/fmax on doubles cost three times as many instructions)
+                    const bool loz = !(inz[u] >= 0.0), hiz = inz[u] > limz;         // NaN counts as "low"
+                    const bool loy = !(iny[u] >= 0.0), hiy = iny[u] > limy;
+                    const bool lox = !(inx[u] >= 0.0), hix = inx[u] > limx;
+                    double cz = loz ? 0.0 : (hiz ? limz : inz[u]);
+                    double cy = loy ? 0.0 : (hiy ? limy : iny[u]);
+                    double cx = lox ? 0.0 : (hix ? limx : inx[u]);
+                    const bool inr = !(loz | hiz | loy | hiy | lox | hix);
                     bool mapped_danger = false, nanflag = false;
                     if (!cmode && !inr) {
                         // boundary map of the out-of-range axes, out of line (deform.c:47-128); the mapped
                         // coordinate is in [0, len-1] (reflect: possibly in (-1, 0), handled by the mirror taps)
-                        if (cz != inz[u]) { mapped_danger |= edf_near_half_integer(inz[u]); cz = edf_map_coordinate_cold(inz[u], lenz, d.mode); }
-                        if (cy != iny[u]) { mapped_danger |= edf_near_half_integer(iny[u]); cy = edf_map_coordinate_cold(iny[u], leny, d.mode); }
-                        if (cx != inx[u]) { mapped_danger |= edf_near_half_integer(inx[u]); cx = edf_map_coordinate_cold(inx[u], lenx, d.mode); }
+                        if (loz | hiz) { mapped_danger |= edf_near_half_integer(inz[u]); cz = edf_map_coordinate_cold(inz[u], lenz, d.mode); }
+                        if (loy | hiy) { mapped_danger |= edf_near_half_integer(iny[u]); cy = edf_map_coordinate_cold(iny[u], leny, d.mode); }
+                        if (lox | hix) { mapped_danger |= edf_near_half_integer(inx[u]); cx = edf_map_coordinate_cold(inx[u], lenx, d.mode); }
                         if (!((cz > -1.0) & (cy > -1.0) & (cx > -1.0))) { nanflag = true; cz = cy = cx = 0.0; }   // NaN
                     }
                     const double flz = (ORDER & 1) ? floor(cz) : floor(xadd(cz, 0.5));
@@ -467,7 +485,8 @@ edf_lean3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
                     }
                     slow[u] = valid[u] & ((gate & ((inr | !cmode) ? danger : nearmiss)) | nanflag);
                     cst[u] = valid[u] & !inr & cmode & !slow[u];
-                    any_ex |= (stx[u] < 0) | (stx[u] + ORDER >= lenx);
+                    any_ex |= (stx[u] < 0) | (stx[u] + ORDER >= lenx) | (sty[u] < 0) | (sty[u] + ORDER >= leny) |
+                              (stz[u] < 0) | (stz[u] + ORDER >= lenz);
                 }
                 // ---- phase 2: tap offsets (single-reflection mirror at the edges) and weights
                 float t[U];
@@ -478,29 +497,26 @@ edf_lean3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
                         t[u] = __ldg(pin + (edf_mirror1(stz[u], lenz) * isz + edf_mirror1(sty[u], leny) * isy +
                                             edf_mirror1(stx[u], lenx)));
                 } else {
-                    int oz[U][NT], oy[U][NT];
                     float wz[U][NT], wy[U][NT], wxf[U][NT];
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-#pragma unroll
-                        for (int i = 0; i < NT; ++i) {
-                            oz[u][i] = edf_mirror1(stz[u] + i, lenz) * isz;
-                            oy[u][i] = edf_mirror1(sty[u] + i, leny) * isy;
-                        }
                         edf_bspline_weights_f32<ORDER>(fz[u], wz[u]);
                         edf_bspline_weights_f32<ORDER>(fy[u], wy[u]);
                         edf_bspline_weights_f32<ORDER>(fx[u], wxf[u]);
                     }
                     if (!warp_ex) {
+                        // every window of the warp lies inside the volume: one base pointer per voxel, rows at
+                        // warp-uniform distances (i * isz + j * isy), x taps at immediate offsets
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
+                            const float* b0 = pin + (stz[u] * isz + sty[u] * isy + stx[u]);
                             float acc = 0.f;
 #pragma unroll
                             for (int i = 0; i < NT; ++i) {
                                 float ti = 0.f;
 #pragma unroll
                                 for (int j = 0; j < NT; ++j) {
-                                    const float* r = pin + (oz[u][i] + oy[u][j] + stx[u]);
+                                    const float* r = b0 + (i * isz + j * isy);
                                     float tj = __ldg(r) * wxf[u][0];
 #pragma unroll
                                     for (int k = 1; k < NT; ++k) tj = fmaf(__ldg(r + k), wxf[u][k], tj);
@@ -511,18 +527,23 @@ edf_lean3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
                             t[u] = acc;
                         }
                     } else {
+                        // some window of the warp crosses the border of the volume: mirrored taps on all axes
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
-                            int oxk[NT];
+                            int oz[NT], oy[NT], oxk[NT];
 #pragma unroll
-                            for (int k = 0; k < NT; ++k) oxk[k] = edf_mirror1(stx[u] + k, lenx);
+                            for (int i = 0; i < NT; ++i) {
+                                oz[i] = edf_mirror1(stz[u] + i, lenz) * isz;
+                                oy[i] = edf_mirror1(sty[u] + i, leny) * isy;
+                                oxk[i] = edf_mirror1(stx[u] + i, lenx);
+                            }
                             float acc = 0.f;
 #pragma unroll
                             for (int i = 0; i < NT; ++i) {
                                 float ti = 0.f;
 #pragma unroll
                                 for (int j = 0; j < NT; ++j) {
-                                    const float* r = pin + (oz[u][i] + oy[u][j]);
+                                    const float* r = pin + (oz[i] + oy[j]);
                                     float tj = __ldg(r + oxk[0]) * wxf[u][0];
 #pragma unroll
                                     for (int k = 1; k < NT; ++k) tj = fmaf(__ldg(r + oxk[k]), wxf[u][k], tj);
@@ -570,8 +591,8 @@ static void edf_lean_launch(int order, int gradient, dim3 grid, cudaStream_t st,
         switch (order) {
         case 0: edf_lean3d_fwd_kernel<0, 4><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
         case 1: edf_lean3d_fwd_kernel<1, 4><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
-        case 2: edf_lean3d_fwd_kernel<2, 2><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
-        case 3: edf_lean3d_fwd_kernel<3, 2><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
+        case 2: edf_lean3d_fwd_kernel<2, EDF_LEAN_FWD_U3><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
+        case 3: edf_lean3d_fwd_kernel<3, EDF_LEAN_FWD_U3><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
         case 4: edf_lean3d_fwd_kernel<4, 1><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
         default: edf_lean3d_fwd_kernel<5, 1><<<grid, EDF_FAST_THREADS, 0, st>>>(p, L, ii); break;
         }
@@ -602,15 +623,22 @@ static void edf_lean_launch(int order, int gradient, dim3 grid, cudaStream_t st,
 // or does not fit the accumulation window fall back to direct global atomics.
 // =======================================================================================
 #define EDF_GW_TX 32               // x positions per warp / CTA
+#ifndef EDF_GW_G
 #define EDF_GW_G 4                 // z-slabs per CTA
+#endif
 #define EDF_GW_RG 2                // row groups: warp w owns slab (w % G) and rows rg*MR .. rg*MR+MR-1 of a chunk
 #define EDF_GW_MR (EDF_FAST_M / EDF_GW_RG)
 #define EDF_GW_WARPS (EDF_GW_G * EDF_GW_RG)
 #define EDF_GW_THREADS (EDF_GW_TX * EDF_GW_WARPS)
+#ifndef EDF_GW_MINB
+#define EDF_GW_MINB 2              // CTAs per SM the kernel is compiled for
+#endif
 #define EDF_GW_NC 8                // control-point span capacity of this kernel's tables
+#ifndef EDF_GW_WZ
 #define EDF_GW_WZ 19               // accumulation window (cells of dX) around the chunk's footprint:
 #define EDF_GW_WY 23               //   tile extent + taps + ~0.2 x (other extents) + margins
 #define EDF_GW_WX 52               // multiple of 4: the flush moves 16-byte groups
+#endif
 #define EDF_GW_MARGIN 2
 #define EDF_GW_FIX 24              // chunk max |dY| maps into [2^(FIX-1), 2^FIX]
 
@@ -654,6 +682,13 @@ __device__ __forceinline__ void edf_gw_coords(const EdfParams& p, const double (
     }
 }
 
+// fixed-point rounding of g * w for the window accumulators: round-to-nearest-even of the exact product
+// through the 1.5 * 2^23 magic add (|g * w| < 2^22)
+__device__ __forceinline__ int edf_gw_round(float g, float w)
+{
+    return __float_as_int(fmaf(g, w, 12582912.0f)) - 0x4B400000;
+}
+
 // rare voxel of the window gradient (next to a rounding / boundary threshold): reference-order
 // re-evaluation, then the general scatter with global atomics
 template <int ORDER>
@@ -677,7 +712,7 @@ __device__ __noinline__ void edf_gradwin_slow_voxel(const EdfParams& p, const Ed
 // instruction traps with cudaErrorIllegalInstruction on this pool's B200 boxes, also in the
 // stand-alone reproducer scripts/experiments/tma_reduce_test.cu, so the row form is used.
 template <int ORDER, int FLUSH>
-__global__ void __launch_bounds__(EDF_GW_THREADS, 2)
+__global__ void __launch_bounds__(EDF_GW_THREADS, EDF_GW_MINB)
 edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -769,16 +804,25 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
         const int yc0 = y0 + c * EDF_FAST_M;
         const int mlast = min(EDF_FAST_M - 1, ody - 1 - yc0);
         // ---- warp-private y-contraction for this warp's rows of the chunk
-        for (int e = lane; e < 3 * EDF_GW_MR * nx; e += 32) {
-            const int jx = e % nx;
-            const int m = (e / nx) % EDF_GW_MR;
-            const int h = e / (nx * EDF_GW_MR);
+        {
+            // lane -> (row m, phase q); the 3 * nx (component, column) pairs go round the phases (no division)
+            static_assert(EDF_GW_MR == 4, "lane mapping of the B table assumes 4 rows per warp");
+            const int m = lane & 3, q = lane >> 2;
             const int row = c * EDF_FAST_M + rg * EDF_GW_MR + m;
             const int r0 = s.sy[row] - sy_min;
-            double b = 0.0;
+            double wyr[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b = fma(s.A[h][g][r0 + j][jx], s.wy[row][j], b);
-            Bw[h][m][jx] = b;
+            for (int j = 0; j < 4; ++j) wyr[j] = s.wy[row][j];
+            int h = 0, jx = q;
+            while (jx >= nx) { jx -= nx; ++h; }
+            while (h < 3) {
+                double b = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b = fma(s.A[h][g][r0 + j][jx], wyr[j], b);
+                Bw[h][m][jx] = b;
+                jx += 8;
+                while (jx >= nx) { jx -= nx; ++h; }
+            }
         }
         if (tid == 0) { s.wmin[0] = s.wmin[1] = s.wmin[2] = 0x7fffffff; s.gmax_bits = 0; }
         __syncthreads();
@@ -816,8 +860,11 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
             // power-of-two scale: max|dY| of the chunk -> [2^(FIX-1), 2^FIX]
             int ex;
             frexpf(gmax_c, &ex);                                  // gmax = f * 2^ex, f in [0.5, 1)
-            const float scale = ldexpf(1.0f, EDF_GW_FIX - ex);
-            const float inv_scale = ldexpf(1.0f, ex - EDF_GW_FIX);
+            // orders >= 2 convert with the magic-number add (FFMA + IADD; F2I runs at a quarter of the rate on
+            // the XU pipe), which holds |v| < 2^22: one bit less of scale there (largest weight product 0.42)
+            constexpr int FIX = (ORDER >= 2) ? EDF_GW_FIX - 1 : EDF_GW_FIX;
+            const float scale = ldexpf(1.0f, FIX - ex);
+            const float inv_scale = ldexpf(1.0f, ex - FIX);
             const int wz0 = s.wmin[0] - (ORDER + 1) / 2 - EDF_GW_MARGIN;
             const int wy0 = s.wmin[1] - (ORDER + 1) / 2 - EDF_GW_MARGIN;
             const int wx0 = (s.wmin[2] - (ORDER + 1) / 2 - EDF_GW_MARGIN) & ~3;   // 16-byte aligned columns
@@ -967,26 +1014,65 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
                     }
                     const bool edge = (stz < 0) | (stz + ORDER >= lenz) | (sty < 0) | (sty + ORDER >= leny) |
                                       (stx < 0) | (stx + ORDER >= lenx);
-                    const int rz = stz - wz0, ry = sty - wy0, rx = stx - wx0;
-                    const bool inwin = (rz >= 0) & (rz + ORDER < EDF_GW_WZ) & (ry >= 0) & (ry + ORDER < EDF_GW_WY) &
-                                       (rx >= 0) & (rx + ORDER < EDF_GW_WX);
-                    if (!edge && inwin) {
-                        int* wbase = s.win + ((rz * EDF_GW_WY + ry) * EDF_GW_WX + rx);
-                        const float gs = gval * scale;
+                    // a warp with a border voxel takes the mirrored-index form for all its lanes (identical
+                    // results: the mirror of an inside index is the index itself)
+                    const bool wedge = __any_sync(__activemask(), edge);
+                    const float gs = gval * scale;
+                    bool done = false;
+                    if (!wedge) {
+                        const int rz = stz - wz0, ry = sty - wy0, rx = stx - wx0;
+                        const bool inwin = (rz >= 0) & (rz + ORDER < EDF_GW_WZ) & (ry >= 0) & (ry + ORDER < EDF_GW_WY) &
+                                           (rx >= 0) & (rx + ORDER < EDF_GW_WX);
+                        if (inwin) {
+                            int* wbase = s.win + ((rz * EDF_GW_WY + ry) * EDF_GW_WX + rx);
 #pragma unroll
-                        for (int i = 0; i < NT; ++i) {
-                            const float gi = (ORDER > 0) ? gs * wzf[i] : gs;
+                            for (int i = 0; i < NT; ++i) {
+                                const float gi = gs * wzf[i];
 #pragma unroll
-                            for (int j = 0; j < NT; ++j) {
-                                const float gj = (ORDER > 0) ? gi * wyf[j] : gi;
-                                int* r = wbase + (i * EDF_GW_WY + j) * EDF_GW_WX;
+                                for (int j = 0; j < NT; ++j) {
+                                    const float gj = gi * wyf[j];
+                                    int* r = wbase + (i * EDF_GW_WY + j) * EDF_GW_WX;
 #pragma unroll
-                                for (int k = 0; k < NT; ++k)
-                                    atomicAdd(r + k, __float2int_rn((ORDER > 0) ? gj * wxf[k] : gj));
+                                    for (int k = 0; k < NT; ++k)
+                                        atomicAdd(r + k, edf_gw_round(gj, wxf[k]));
+                                }
                             }
+                            done = true;
                         }
                     } else {
-                        // border of the volume / outside the accumulation window: direct global atomics
+                        int rzi[NT], ryi[NT], rxi[NT];
+                        bool inw = true;
+#pragma unroll
+                        for (int i = 0; i < NT; ++i) {
+                            rzi[i] = edf_mirror1(stz + i, lenz) - wz0;
+                            ryi[i] = edf_mirror1(sty + i, leny) - wy0;
+                            rxi[i] = edf_mirror1(stx + i, lenx) - wx0;
+                            inw &= ((unsigned)rzi[i] < (unsigned)EDF_GW_WZ) & ((unsigned)ryi[i] < (unsigned)EDF_GW_WY) &
+                                   ((unsigned)rxi[i] < (unsigned)EDF_GW_WX);
+                            rzi[i] *= EDF_GW_WY * EDF_GW_WX;
+                            ryi[i] *= EDF_GW_WX;
+                        }
+                        // single reflection suffices only while the window start is within one length of the volume
+                        inw &= (stz >= -lenz) & (stz + ORDER < 2 * lenz - 1) & (sty >= -leny) & (sty + ORDER < 2 * leny - 1) &
+                               (stx >= -lenx) & (stx + ORDER < 2 * lenx - 1);
+                        if (inw) {
+#pragma unroll
+                            for (int i = 0; i < NT; ++i) {
+                                const float gi = gs * wzf[i];
+#pragma unroll
+                                for (int j = 0; j < NT; ++j) {
+                                    const float gj = gi * wyf[j];
+                                    int* r = s.win + (rzi[i] + ryi[j]);
+#pragma unroll
+                                    for (int k = 0; k < NT; ++k)
+                                        atomicAdd(r + rxi[k], edf_gw_round(gj, wxf[k]));
+                                }
+                            }
+                            done = true;
+                        }
+                    }
+                    if (!done) {
+                        // outside the accumulation window: direct global atomics
                         int ozt[NT], oyt[NT], oxt[NT];
 #pragma unroll
                         for (int i = 0; i < NT; ++i) {
@@ -1051,16 +1137,30 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
                 __syncthreads();
                 if (tid < (EDF_GW_WZ * EDF_GW_WY + 31) / 32 + 1) s.rowmask[tid] = 0;
             } else if (FLUSH == 1) {
+                // 16-byte group q = tid, tid + THREADS, ...: (plane, row, group-in-row) advance incrementally
+                constexpr int GPR = EDF_GW_WX / 4;                                  // groups per row
+                constexpr int DG = EDF_GW_THREADS % GPR, DR = EDF_GW_THREADS / GPR;  // step in groups / rows
+                static_assert(DR + 1 < 2 * EDF_GW_WY, "at most two row wraps per step");
+                int cg = tid % GPR, iy = (tid / GPR) % EDF_GW_WY, iz = tid / (GPR * EDF_GW_WY);
                 for (int q = tid; q < NWIN / 4; q += EDF_GW_THREADS) {
                     int4 v = reinterpret_cast<int4*>(s.win)[q];
                     if ((v.x | v.y | v.z | v.w) != 0) {
                         reinterpret_cast<int4*>(s.win)[q] = make_int4(0, 0, 0, 0);
-                        const int ix = (q % (EDF_GW_WX / 4)) * 4;
-                        const int iy = (q / (EDF_GW_WX / 4)) % EDF_GW_WY;
-                        const int iz = q / ((EDF_GW_WX / 4) * EDF_GW_WY);
-                        float4* dst = reinterpret_cast<float4*>(pdx + ((wz0 + iz) * isz + (wy0 + iy) * isy + (wx0 + ix)));
+                        float4* dst = reinterpret_cast<float4*>(pdx + ((wz0 + iz) * isz + (wy0 + iy) * isy + (wx0 + 4 * cg)));
                         atomicAdd(dst, make_float4((float)v.x * inv_scale, (float)v.y * inv_scale,
                                                    (float)v.z * inv_scale, (float)v.w * inv_scale));
+                    }
+                    cg += DG;
+                    const int carry = cg >= GPR;
+                    cg -= carry ? GPR : 0;
+                    iy += DR + carry;
+                    int wrap = iy >= EDF_GW_WY;
+                    iy -= wrap ? EDF_GW_WY : 0;
+                    iz += wrap;
+                    if (DR + 1 >= EDF_GW_WY) {
+                        wrap = iy >= EDF_GW_WY;
+                        iy -= wrap ? EDF_GW_WY : 0;
+                        iz += wrap;
                     }
                 }
             } else {
