@@ -18,6 +18,7 @@ EDF_MAX_AXIS = 4
 EDF_MAX_INPUTS = 8
 
 EDF_FLAG_FORCE_GENERIC = 1
+EDF_FLAG_NO_WINDOW = 2
 
 # numpy dtype -> edf_dtype (the 11 distinct element types of deform.c:863-888)
 _DTYPE_CODES = {

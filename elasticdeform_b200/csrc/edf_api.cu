@@ -86,7 +86,7 @@ static int run_problem(const edf_problem* pr, int gradient, cudaStream_t st)
     if (!(pr->flags & EDF_FLAG_FORCE_GENERIC)) {
         const char* name = nullptr;
         uint32_t handled = 0;
-        rc = edf_fast_try_launch(p, st, &name, &handled);
+        rc = edf_fast_try_launch(p, st, &name, &handled, pr->flags);
         if (rc < 0) return edf_fail(EDF_ERR_CUDA, "fast kernel launch failed: %s",
                                     cudaGetErrorString(g_fast_launch_error));
         if (rc > 0) {

@@ -560,8 +560,9 @@ static bool edf_gradwin_eligible(const EdfParams& p);
 //   *handled_mask receives the inputs that were processed (the caller runs the generic
 //   kernel for the others); returns the number of kernels launched, or <0 on a launch error.
 static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char** name,
-                               uint32_t* handled_mask)
+                               uint32_t* handled_mask, uint32_t flags)
 {
+    const bool windows = !(flags & EDF_FLAG_NO_WINDOW);
     *handled_mask = 0;
     if (p.naxis != 2 && p.naxis != 3) return 0;
     const int AX = p.naxis - 1, AY = p.naxis - 2;
@@ -597,7 +598,7 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
             L.rows_per_cta = ry;
             dim3 lgrid = grid;
             lgrid.y = (unsigned)((p.odim[AY] + ry - 1) / ry);
-            if (p.gradient && edf_gradwin_eligible(p)) {
+            if (windows && p.gradient && edf_gradwin_eligible(p)) {
                 const int rcw = edf_lean_launch_gradwin(p.inp[ii].order, st, p, L, ii);
                 if (rcw < 0) return -1;
                 *name = rcw == 2 ? "lean3d_f32_gradwin_tma" : "lean3d_f32_gradwin";

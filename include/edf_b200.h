@@ -101,6 +101,7 @@ typedef struct {
 
 /* flags */
 #define EDF_FLAG_FORCE_GENERIC 1u     /* debug: never take a specialised kernel */
+#define EDF_FLAG_NO_WINDOW     2u     /* debug: direct gather / scatter kernels, no shared-memory window */
 
 int edf_deform_grid(const edf_problem* problem, void* stream);
 int edf_deform_grid_grad(const edf_problem* problem, void* stream);
