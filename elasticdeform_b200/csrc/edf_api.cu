@@ -14,6 +14,7 @@
 #include "edf_host.h"
 #include "edf_fast.cuh"
 #include "edf_lean.cuh"
+#include "edf_swin.cuh"
 
 // ----------------------------------------------------------------------------
 // error plumbing

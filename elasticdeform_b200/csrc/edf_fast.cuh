@@ -555,6 +555,9 @@ static void edf_lean_launch(int order, int gradient, dim3 grid, cudaStream_t st,
                             const EdfFastLaunch& L, int ii);
 static int edf_lean_launch_gradwin(int order, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii);
 static bool edf_gradwin_eligible(const EdfParams& p);
+static bool edf_swin_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii);
+static bool edf_swin_grad_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii, bool all_orders);
+static int edf_swin_launch(int order, int gradient, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii);
 
 // Tries to run (part of) the problem on the specialised kernels.
 //   *handled_mask receives the inputs that were processed (the caller runs the generic
@@ -598,7 +601,16 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
             L.rows_per_cta = ry;
             dim3 lgrid = grid;
             lgrid.y = (unsigned)((p.odim[AY] + ry - 1) / ry);
-            if (windows && p.gradient && edf_gradwin_eligible(p)) {
+            int rcs = -2;
+            if (windows && !p.gradient && (flags & EDF_FLAG_STAGED_FWD) && edf_swin_eligible(p, L, ii))
+                rcs = edf_swin_launch(p.inp[ii].order, 0, st, p, L, ii);   // staged-window gather (edf_swin.cuh), opt-in
+            else if (windows && p.gradient && !(flags & EDF_FLAG_FIXED_WINDOW) &&
+                     edf_swin_grad_eligible(p, L, ii, (flags & EDF_FLAG_STAGED_ALL) != 0))
+                rcs = edf_swin_launch(p.inp[ii].order, 1, st, p, L, ii);   // staged-window scatter (edf_swin.cuh)
+            if (rcs == -1) return -1;
+            if (rcs == 0) {
+                *name = p.gradient ? "swin3d_f32_grad" : "swin3d_f32";
+            } else if (windows && p.gradient && edf_gradwin_eligible(p)) {
                 const int rcw = edf_lean_launch_gradwin(p.inp[ii].order, st, p, L, ii);
                 if (rcw < 0) return -1;
                 *name = rcw == 2 ? "lean3d_f32_gradwin_tma" : "lean3d_f32_gradwin";

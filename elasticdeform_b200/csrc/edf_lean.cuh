@@ -863,8 +863,14 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
             // orders >= 2 convert with the magic-number add (FFMA + IADD; F2I runs at a quarter of the rate on
             // the XU pipe), which holds |v| < 2^22: one bit less of scale there (largest weight product 0.42)
             constexpr int FIX = (ORDER >= 2) ? EDF_GW_FIX - 1 : EDF_GW_FIX;
-            const float scale = ldexpf(1.0f, FIX - ex);
-            const float inv_scale = ldexpf(1.0f, ex - FIX);
+            // orders >= 2: the largest possible contribution (max|dY| times the largest weight product of the
+            // order) maps to just under 2^22, the range of the magic-number rounding: 1.2-6x finer than the
+            // power-of-two scale, which matters once the prefilter adjoint amplifies the rounding noise
+            constexpr float WMAX = (ORDER <= 1) ? 1.0f : (ORDER == 2) ? 0.75f : (ORDER == 3) ? (2.0f / 3.0f)
+                                 : (ORDER == 4) ? (115.0f / 192.0f) : 0.55f;
+            const float scale = (ORDER >= 2) ? (4194304.0f * 0.999f) / (fmaxf(gmax_c, 1e-30f) * (WMAX * WMAX * WMAX))
+                                             : ldexpf(1.0f, FIX - ex);
+            const float inv_scale = (ORDER >= 2) ? 1.0f / scale : ldexpf(1.0f, ex - FIX);
             const int wz0 = s.wmin[0] - (ORDER + 1) / 2 - EDF_GW_MARGIN;
             const int wy0 = s.wmin[1] - (ORDER + 1) / 2 - EDF_GW_MARGIN;
             const int wx0 = (s.wmin[2] - (ORDER + 1) / 2 - EDF_GW_MARGIN) & ~3;   // 16-byte aligned columns

@@ -1,0 +1,882 @@
+// edf_swin.cuh -- forward gather through a STAGED shared-memory window (K1 for orders >= 2).
+//
+// Why: the direct gather (edf_lean3d_fwd_kernel) issues (order+1)^3 scalar global loads per voxel;
+// the 32 windows of a warp straddle 3.4 cache lines per load instruction and the L1 replays a load
+// once per line at ~2 cycles per replay, which is what bounds it (0.64 ms for 256^3 at order 3:
+// 114 M wavefronts / 148 SMs x 1.8 cycles).  Shared memory serves a warp load in ONE cycle as long
+// as the 32 lanes hit 32 different banks, so this kernel first copies the part of the input volume
+// a chunk of output voxels can reach into shared memory and gathers from there:
+//
+//   CTA = 8 warps = 8 z-slabs x 32 x positions, walking along y in chunks of 4 rows (1024 voxels).
+//   Per chunk: (A) every thread runs the coordinate pipeline of its 4 voxels (fp64 separable
+//   B-spline of the control grid, boundary classification, window start + fractional offset; rare
+//   voxels next to a rounding threshold are redone in the reference order, as in the lean kernel);
+//   (B) warp REDUX + shared atomics give the EXACT bounding box of the chunk's tap windows;
+//   (C) the box is copied from the volume with 16-byte cp.async (LDGSTS, L2 -> shared memory, no
+//   registers; 16 lanes per window row), rows outside the volume resolved through the reference's
+//   mirror map of edge taps (deform.c:791-813) at staging time, so the gather itself has no border
+//   case; (D) every voxel reads its (order+1)^3 taps with LDS at immediate offsets from one base
+//   address per z-tap plane.  The window rows are 64 floats apart: the bank of a tap is its x index
+//   mod 32, and neighbouring lanes have neighbouring x indices whatever their y / z rows are, so
+//   the loads do not collide under shear (what remains: a warp whose 32 windows span more than 32
+//   columns -- a locally stretching field -- needs two wavefronts per load).
+//   The window has a fixed capacity (EDF_SW_ROWS rows of 64 floats) and dynamic extents.  A chunk
+//   whose box does not fit (very steep field) is gathered straight from global memory by the
+//   single-voxel routine.  Between the barriers a thread keeps 4 registers per voxel (the three
+//   window starts packed into one word + three fractional offsets).
+//   Two CTAs per SM: one CTA's staging / coordinate phase overlaps the other's gather.
+//
+// Results are bit-identical to edf_lean3d_fwd_kernel (same weights, same FMA order).
+#pragma once
+#include "edf_lean.cuh"
+#include <limits.h>
+
+#define EDF_SW_TX 32               // x positions per warp / CTA
+#define EDF_SW_G 8                 // z-slabs per CTA (one warp each)
+#define EDF_SW_MR 4                // rows per chunk
+#define EDF_SW_THREADS (EDF_SW_TX * EDF_SW_G)
+#define EDF_SW_RY 32               // rows a CTA walks through (table capacity)
+#define EDF_SW_NC 8                // control-point span capacity of the tables
+#define EDF_SW_PITCH 64            // floats between window rows: multiple of 32 -> bank = x index mod 32
+#ifndef EDF_SW_ROWS
+#define EDF_SW_ROWS 364            // window capacity in rows; 2 CTAs x 112 KB per SM
+#endif
+#define EDF_SW_MAXQ (EDF_SW_PITCH / 4)
+#ifndef EDF_SWIN_GRAD_MAXORDER
+#define EDF_SWIN_GRAD_MAXORDER 3      // highest spline order the staged-window gradient kernel takes over by default
+#endif                                //   (measured on B200, 256^3: 0.24 / 0.27 / 0.47 / 0.77 ms at orders 0-3 against
+                                      //   0.35 / 0.39 / 0.57 / 0.78 ms for the fixed window; 7 % slower at order 5)
+
+static_assert(EDF_SW_MR == EDF_GW_MR && EDF_SW_NC == EDF_GW_NC, "edf_gw_coords is shared with the window gradient");
+
+struct EdfSwinSmem {
+    double wz[EDF_SW_G][4];
+    double wy[EDF_SW_RY][4];
+    double wx[EDF_SW_TX][4];
+    int    sz[EDF_SW_G];
+    int    sy[EDF_SW_RY];
+    int    sx[EDF_SW_TX];
+    int    ny, nx, nonzero, pad_;
+    int    bb[3][8];                // [chunk % 3]: min z,y,x start, max z,y,x start of the chunk's active voxels
+    double A[3][EDF_SW_G][EDF_SW_NC][EDF_SW_NC];
+    double Bw[EDF_SW_G][3][EDF_SW_MR][EDF_SW_NC];
+    __align__(128) float win[EDF_SW_ROWS * EDF_SW_PITCH];
+};
+
+__device__ __forceinline__ void edf_cp_async16(uint32_t smem_dst, const float* gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void edf_cp_async4(uint32_t smem_dst, const float* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+// exact floor / window start / fractional offset without conversion instructions for the floor:
+// RD(v + 1.5 * 2^52) has floor(v) in its low mantissa bits (|v| < 2^31)
+template <int ORDER>
+__device__ __forceinline__ void edf_floor_split(double c, int& start, float& frac)
+{
+    const double M = 6755399441055744.0;
+    const double v = (ORDER & 1) ? c : xadd(c, 0.5);
+    const double t = __dadd_rd(v, M);
+    const double fl = __dsub_rn(t, M);
+    start = __double2loint(t) - ORDER / 2;
+    frac = (float)xsub(c, fl);
+}
+
+// per-voxel state kept across the staging barrier: the three window starts relative to the voxel's own
+// index, 10 bits each (displacements beyond +-511 voxels take the single-voxel routine)
+#define EDF_SW_PK_BIAS 512
+__device__ __forceinline__ bool edf_swin_pack(int dz, int dy, int dx, unsigned& pk)
+{
+    const unsigned a = (unsigned)(dz + EDF_SW_PK_BIAS), b = (unsigned)(dy + EDF_SW_PK_BIAS), c = (unsigned)(dx + EDF_SW_PK_BIAS);
+    pk = (a << 20) | ((b & 1023u) << 10) | (c & 1023u);
+    return (a < 1024u) & (b < 1024u) & (c < 1024u);
+}
+
+// Coordinate pipeline of one voxel (shared by the forward and the gradient kernel): table coordinates, range
+// classification, boundary map (non-constant modes, out of line), window starts and fractional offsets.
+// `slow`: the voxel sits next to a rounding / boundary threshold (or is NaN) and must be redone by the
+// single-voxel routine in the reference order; `cst`: it takes the constant value (deform.c:782, :819-823).
+template <int ORDER, bool CMODE>
+__device__ __forceinline__ void edf_swin_voxel(const EdfParams& p, int mode, const double (*Bw)[EDF_SW_MR][EDF_SW_NC],
+                                               int u, int sxrel, const double* wx, bool affine, int z, int y, int x,
+                                               double bz, double bx, double offy, double limz, double limy, double limx,
+                                               int lenz, int leny, int lenx, bool gate,
+                                               int& stz, int& sty, int& stx, float& fz, float& fy, float& fx,
+                                               bool& slow, bool& cst, bool& oob)
+{
+    double inz, iny, inx;
+    edf_gw_coords(p, Bw, u, sxrel, wx, affine, z, y, x, bz, bx, offy, inz, iny, inx);
+    const bool loz = !(inz >= 0.0), hiz = inz > limz;         // NaN counts as "low"
+    const bool loy = !(iny >= 0.0), hiy = iny > limy;
+    const bool lox = !(inx >= 0.0), hix = inx > limx;
+    double cz = loz ? 0.0 : (hiz ? limz : inz);
+    double cy = loy ? 0.0 : (hiy ? limy : iny);
+    double cx = lox ? 0.0 : (hix ? limx : inx);
+    const bool inr = !(loz | hiz | loy | hiy | lox | hix);
+    bool mapped_danger = false, nanflag = false;
+    if (!CMODE && !inr) {
+        // boundary map of the out-of-range axes, out of line (deform.c:47-128)
+        if (loz | hiz) { mapped_danger |= edf_near_half_integer(inz); cz = edf_map_coordinate_cold(inz, lenz, mode); }
+        if (loy | hiy) { mapped_danger |= edf_near_half_integer(iny); cy = edf_map_coordinate_cold(iny, leny, mode); }
+        if (lox | hix) { mapped_danger |= edf_near_half_integer(inx); cx = edf_map_coordinate_cold(inx, lenx, mode); }
+        if (!((cz > -1.0) & (cy > -1.0) & (cx > -1.0))) { nanflag = true; cz = cy = cx = 0.0; }   // NaN
+    }
+    edf_floor_split<ORDER>(cz, stz, fz);
+    edf_floor_split<ORDER>(cy, sty, fy);
+    edf_floor_split<ORDER>(cx, stx, fx);
+    bool danger;
+    if (ORDER & 1)
+        danger = (fz < EDF_LEAN_EPSF) | (fz > 1.0f - EDF_LEAN_EPSF) | (fy < EDF_LEAN_EPSF) |
+                 (fy > 1.0f - EDF_LEAN_EPSF) | (fx < EDF_LEAN_EPSF) | (fx > 1.0f - EDF_LEAN_EPSF);
+    else
+        danger = (fabsf(fz) < EDF_LEAN_EPSF) | (fabsf(fz) > 0.5f - EDF_LEAN_EPSF) |
+                 (fabsf(fy) < EDF_LEAN_EPSF) | (fabsf(fy) > 0.5f - EDF_LEAN_EPSF) |
+                 (fabsf(fx) < EDF_LEAN_EPSF) | (fabsf(fx) > 0.5f - EDF_LEAN_EPSF);
+    danger |= mapped_danger;
+    bool nearmiss = false;
+    if (CMODE) {
+        const double qz = fabs(xsub(inz, cz)), qy = fabs(xsub(iny, cy)), qx = fabs(xsub(inx, cx));
+        nearmiss = ((qz > 0.0) & (qz < EDF_FAST_EPS)) | ((qy > 0.0) & (qy < EDF_FAST_EPS)) |
+                   ((qx > 0.0) & (qx < EDF_FAST_EPS));
+    }
+    oob = !inr;
+    cst = !inr & CMODE;
+    slow = (gate & ((inr | !CMODE) ? danger : nearmiss)) | nanflag;
+}
+
+// Direct forms for the chunks whose box does not fit the window (very steep fields): the taps straight
+// from / to global memory with the reference's mirror map of edge taps, same weights and FMA order as the
+// window forms (and as edf_lean3d_fwd_kernel).
+template <int ORDER>
+__device__ __forceinline__ float edf_swin_direct_gather(const float* __restrict__ pin, int stz, int sty, int stx,
+                                                        float fz, float fy, float fx, int lenz, int leny, int lenx,
+                                                        int isz, int isy)
+{
+    constexpr int NT = ORDER + 1;
+    int oz[NT], oy[NT], ox[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        oz[i] = edf_mirror1(stz + i, lenz) * isz;
+        oy[i] = edf_mirror1(sty + i, leny) * isy;
+        ox[i] = edf_mirror1(stx + i, lenx);
+    }
+    float wzf[NT], wyf[NT], wxf[NT];
+    edf_bspline_weights_f32<ORDER>(fz, wzf);
+    edf_bspline_weights_f32<ORDER>(fy, wyf);
+    edf_bspline_weights_f32<ORDER>(fx, wxf);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        float ti = 0.f;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const float* r = pin + (oz[i] + oy[j]);
+            float tj = __ldg(r + ox[0]) * wxf[0];
+#pragma unroll
+            for (int k = 1; k < NT; ++k) tj = fmaf(__ldg(r + ox[k]), wxf[k], tj);
+            ti = (j == 0) ? tj * wyf[0] : fmaf(tj, wyf[j], ti);
+        }
+        acc = (i == 0) ? ti * wzf[0] : fmaf(ti, wzf[i], acc);
+    }
+    return acc;
+}
+
+template <int ORDER>
+__device__ __forceinline__ void edf_swin_direct_scatter(float* __restrict__ pdx, float g, int stz, int sty, int stx,
+                                                        float fz, float fy, float fx, int lenz, int leny, int lenx,
+                                                        int isz, int isy)
+{
+    constexpr int NT = ORDER + 1;
+    int oz[NT], oy[NT], ox[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        oz[i] = edf_mirror1(stz + i, lenz) * isz;
+        oy[i] = edf_mirror1(sty + i, leny) * isy;
+        ox[i] = edf_mirror1(stx + i, lenx);
+    }
+    float wzf[NT], wyf[NT], wxf[NT];
+    if (ORDER > 0) {
+        edf_bspline_weights_f32<ORDER>(fz, wzf);
+        edf_bspline_weights_f32<ORDER>(fy, wyf);
+        edf_bspline_weights_f32<ORDER>(fx, wxf);
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        const float gi = (ORDER > 0) ? g * wzf[i] : g;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const float gj = (ORDER > 0) ? gi * wyf[j] : gi;
+            float* r = pdx + (oz[i] + oy[j]);
+#pragma unroll
+            for (int k = 0; k < NT; ++k) atomicAdd(r + ox[k], (ORDER > 0) ? gj * wxf[k] : gj);
+        }
+    }
+}
+
+// CMODE: boundary mode 'constant' (out-of-range voxels take cval: no coordinate map, and no call inside
+// the coordinate phase, which keeps its register allocation free of call-crossing live ranges)
+template <int ORDER, bool CMODE>
+__global__ void __launch_bounds__(EDF_SW_THREADS, 2)
+edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    EdfSwinSmem& s = *reinterpret_cast<EdfSwinSmem*>(smem_raw);
+    constexpr int NT = ORDER + 1;
+    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;     // warp = slab
+    const int x0 = blockIdx.x * EDF_SW_TX;
+    const int ry = (int)L.rows_per_cta;
+    const int y0 = blockIdx.y * ry;
+    const int z0 = blockIdx.z * EDF_SW_G;
+
+    // ---- prologue: control tables, z-contraction A of the displacement coefficients, empty boxes
+    if (tid == 0) s.nonzero = 0;
+    if (tid < 3 * 8) (&s.bb[0][0])[tid] = ((tid & 7) < 3) ? INT_MAX : INT_MIN;
+    if (tid < EDF_SW_TX) {
+        edf_fast_ctrl_entry(p, 2, min((int64_t)(x0 + tid), p.odim[2] - 1), s.wx[tid], &s.sx[tid]);
+    } else if (tid < EDF_SW_TX + EDF_SW_RY) {
+        const int t = tid - EDF_SW_TX;
+        edf_fast_ctrl_entry(p, 1, min((int64_t)(y0 + t), p.odim[1] - 1), s.wy[t], &s.sy[t]);
+    } else if (tid < EDF_SW_TX + EDF_SW_RY + EDF_SW_G) {
+        const int t = tid - EDF_SW_TX - EDF_SW_RY;
+        edf_fast_ctrl_entry(p, 0, min((int64_t)(z0 + t), p.odim[0] - 1), s.wz[t], &s.sz[t]);
+    }
+    __syncthreads();
+    {
+        const int sy_min0 = s.sy[0], sx_min0 = s.sx[0];
+        const int ny = s.sy[EDF_SW_RY - 1] - sy_min0 + 4;
+        const int nxx = s.sx[EDF_SW_TX - 1] - sx_min0 + 4;
+        if (tid == 0) { s.ny = ny; s.nx = nxx; }
+        bool nz = false;
+        const int na = 3 * EDF_SW_G * ny * nxx;
+        for (int e = tid; e < na; e += EDF_SW_THREADS) {
+            const int jx = e % nxx;
+            const int jy = (e / nxx) % ny;
+            const int t = (e / (nxx * ny)) % EDF_SW_G;
+            const int h = e / (nxx * ny * EDF_SW_G);
+            const int my = edf_mirror_index32(sy_min0 + jy, (int)p.ncp[1]);
+            const int mx = edf_mirror_index32(sx_min0 + jx, (int)p.ncp[2]);
+            const char* base = p.disp + p.dstr[0] * h + my * p.dstr[2] + mx * p.dstr[3];
+            double a = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int mz = edf_mirror_index32(s.sz[t] + i, (int)p.ncp[0]);
+                const double cf = (p.ddtype == EDF_F64) ? *(const double*)(base + mz * p.dstr[1])
+                                                        : (double)*(const float*)(base + mz * p.dstr[1]);
+                nz |= (cf != 0.0);
+                a = fma(cf, s.wz[t][i], a);
+            }
+            s.A[h][t][jy][jx] = a;
+        }
+        if (nz) s.nonzero = 1;
+    }
+    __syncthreads();
+
+    const int x = x0 + lane, z = z0 + g;
+    const int odz = (int)p.odim[0], ody = (int)p.odim[1], odx = (int)p.odim[2];
+    const bool tok = (x < odx) && (z < odz);
+    double wx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wx[k] = s.wx[lane][k];
+    const int sxrel = s.sx[lane] - s.sx[0];
+    const int nchunk = min(ry / EDF_SW_MR, (ody - y0 + EDF_SW_MR - 1) / EDF_SW_MR);
+    const bool gate = s.nonzero != 0;
+    const int nx = s.nx, sy_min = s.sy[0];
+    double (*Bw)[EDF_SW_MR][EDF_SW_NC] = s.Bw[g];
+
+    const EdfInputDesc& d = p.inp[ii];
+    const float* __restrict__ pin = (const float*)d.in;
+    float* __restrict__ pout = (float*)d.out;
+    const int lenz = (int)p.idim[0], leny = (int)p.idim[1], lenx = (int)p.idim[2];
+    const double limz = p.idim_m1[0], limy = p.idim_m1[1], limx = p.idim_m1[2];
+    const int isz = L.istr_e[ii][0], isy = L.istr_e[ii][1];
+    const int osy = L.ostr_e[ii][1];
+    const int obase_zx = z * L.ostr_e[ii][0] + x * L.ostr_e[ii][2];   // element offsets fit 32 bits (host-checked)
+    const bool affine = p.has_affine != 0;
+    const float cvalf = __uint_as_float((uint32_t)L.cval_bits[ii]);
+    const double bz = xadd((double)z, p.ooff_d[0]);
+    const double bx = xadd((double)x, p.ooff_d[2]);
+    const double offy = p.ooff_d[1];
+    const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(s.win);
+    // staging role of this thread: 16 lanes per window row, one 16-byte group each
+    const int sq = tid & 15, srow = tid >> 4;
+
+    int par = 0;                                                   // c % 3
+    for (int c = 0; c < nchunk; ++c) {
+        const int yc0 = y0 + c * EDF_SW_MR;
+        // ---- warp-private y-contraction for the 4 rows of the chunk (lane -> row m, phase q)
+        {
+            const int m = lane & 3, q = lane >> 2;
+            const int row = c * EDF_SW_MR + m;
+            const int r0 = s.sy[row] - sy_min;
+            double wyr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wyr[j] = s.wy[row][j];
+            int h = 0, jx = q;
+            while (jx >= nx) { jx -= nx; ++h; }
+            while (h < 3) {
+                double b = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b = fma(s.A[h][g][r0 + j][jx], wyr[j], b);
+                Bw[h][m][jx] = b;
+                jx += 8;
+                while (jx >= nx) { jx -= nx; ++h; }
+            }
+        }
+        __syncwarp();
+
+        // ---- phase A: coordinates and classification of this thread's 4 voxels (branch-free, two at a time)
+        unsigned pk[EDF_SW_MR];
+        float fz[EDF_SW_MR], fy[EDF_SW_MR], fx[EDF_SW_MR];
+        unsigned actm = 0, cstm = 0, slowm = 0;
+        int mnz = INT_MAX, mny = INT_MAX, mnx = INT_MAX, mxz = INT_MIN, mxy = INT_MIN, mxx = INT_MIN;
+#pragma unroll
+        for (int u = 0; u < EDF_SW_MR; ++u) {
+            const int y = yc0 + u;
+            const bool valid = tok && (y < ody);
+            int stz, sty, stx;
+            bool slow, cst, oob;
+            edf_swin_voxel<ORDER, CMODE>(p, d.mode, Bw, u, sxrel, wx, affine, z, y, x, bz, bx, offy, limz, limy, limx,
+                                         lenz, leny, lenx, gate, stz, sty, stx, fz[u], fy[u], fx[u], slow, cst, oob);
+            const bool packed = edf_swin_pack(stz - z, sty - y, stx - x, pk[u]);
+            slow = valid & (slow | (!cst & !packed));
+            if (slow) slowm |= 1u << u;
+            if (valid & !slow & cst) cstm |= 1u << u;
+            if (valid & !slow & !cst) {
+                actm |= 1u << u;
+                mnz = min(mnz, stz); mny = min(mny, sty); mnx = min(mnx, stx);
+                mxz = max(mxz, stz); mxy = max(mxy, sty); mxx = max(mxx, stx);
+            }
+        }
+
+        // ---- phase B: exact bounding box of the chunk's tap windows
+        mnz = __reduce_min_sync(0xffffffffu, mnz);
+        mny = __reduce_min_sync(0xffffffffu, mny);
+        mnx = __reduce_min_sync(0xffffffffu, mnx);
+        mxz = __reduce_max_sync(0xffffffffu, mxz);
+        mxy = __reduce_max_sync(0xffffffffu, mxy);
+        mxx = __reduce_max_sync(0xffffffffu, mxx);
+        if (lane == 0 && mnz != INT_MAX) {
+            int* b = s.bb[par];
+            atomicMin(b + 0, mnz); atomicMin(b + 1, mny); atomicMin(b + 2, mnx);
+            atomicMax(b + 3, mxz); atomicMax(b + 4, mxy); atomicMax(b + 5, mxx);
+        }
+        __syncthreads();                                           // box complete; previous chunk's gathers done
+        // the box of chunk c+2 (= chunk c-1's, no longer read) is reset here: chunk c+2's atomics come after
+        // the next chunk's barrier
+        if (tid < 8) s.bb[par == 0 ? 2 : par - 1][tid] = (tid < 3) ? INT_MAX : INT_MIN;
+        const int wz0 = s.bb[par][0], wy0 = s.bb[par][1], wx0 = s.bb[par][2] & ~3;
+        const int nzw = s.bb[par][3] - wz0 + NT, nyw = s.bb[par][4] - wy0 + NT;
+        const int nq = ((s.bb[par][5] + NT - 1 - wx0) >> 2) + 1;
+        const bool empty = s.bb[par][0] > s.bb[par][3];
+        const bool fit = !empty && nq <= EDF_SW_MAXQ && nzw <= EDF_SW_ROWS && nyw <= EDF_SW_ROWS && nzw * nyw <= EDF_SW_ROWS;
+        if (fit) {
+            // ---- phase C: copy the box into the window.  Rows / planes outside the volume are the mirror images
+            //      the reference's edge taps read (deform.c:796-810); 16-byte groups left or right of the volume
+            //      (lenx % 4 == 0: inside or outside as a whole) likewise, element by element.
+            const int rows = nzw * nyw;
+            if (sq < nq) {
+                const int gx = wx0 + 4 * sq;
+                const bool xin = (unsigned)gx < (unsigned)lenx;
+                int r = srow;
+                int zr = (int)__umulhi((unsigned)r, 0xffffffffu / (unsigned)nyw + 1u);      // r / nyw (nyw >= 2)
+                int yr = r - zr * nyw;
+                uint32_t dst = win_s + (uint32_t)(r * EDF_SW_PITCH + 4 * sq) * 4u;
+                if (xin) {
+                    const float* srcx = pin + gx;
+                    for (; r < rows; r += EDF_SW_THREADS / 16) {
+                        const int gz = edf_mirror1(wz0 + zr, lenz), gy = edf_mirror1(wy0 + yr, leny);
+                        edf_cp_async16(dst, srcx + (gz * isz + gy * isy));
+                        dst += (EDF_SW_THREADS / 16) * EDF_SW_PITCH * 4;
+                        yr += EDF_SW_THREADS / 16;
+                        while (yr >= nyw) { yr -= nyw; ++zr; }
+                    }
+                } else {
+                    const int m0 = edf_mirror1(gx, lenx), m1 = edf_mirror1(gx + 1, lenx);
+                    const int m2 = edf_mirror1(gx + 2, lenx), m3 = edf_mirror1(gx + 3, lenx);
+                    for (; r < rows; r += EDF_SW_THREADS / 16) {
+                        const int gz = edf_mirror1(wz0 + zr, lenz), gy = edf_mirror1(wy0 + yr, leny);
+                        const float* src = pin + (gz * isz + gy * isy);
+                        edf_cp_async4(dst, src + m0);
+                        edf_cp_async4(dst + 4, src + m1);
+                        edf_cp_async4(dst + 8, src + m2);
+                        edf_cp_async4(dst + 12, src + m3);
+                        dst += (EDF_SW_THREADS / 16) * EDF_SW_PITCH * 4;
+                        yr += EDF_SW_THREADS / 16;
+                        while (yr >= nyw) { yr -= nyw; ++zr; }
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            // ---- phase D: gather from the window (inactive lanes read cell 0 and discard)
+            const int slab = nyw * EDF_SW_PITCH;
+            const int lin0 = ((z - EDF_SW_PK_BIAS - wz0) * nyw + (yc0 - EDF_SW_PK_BIAS - wy0)) * EDF_SW_PITCH +
+                             (x - EDF_SW_PK_BIAS - wx0);
+#pragma unroll
+            for (int u = 0; u < EDF_SW_MR; ++u) {
+                const bool a = (actm >> u) & 1u;
+                if (!__any_sync(0xffffffffu, a)) continue;
+                const int rz = (int)(pk[u] >> 20), ryw = (int)((pk[u] >> 10) & 1023u), rx = (int)(pk[u] & 1023u);
+                const int off = a ? lin0 + u * EDF_SW_PITCH + (rz * nyw + ryw) * EDF_SW_PITCH + rx : 0;
+                const float* b0 = s.win + off;
+                float wzf[NT], wyf[NT], wxf[NT];
+                edf_bspline_weights_f32<ORDER>(fz[u], wzf);
+                edf_bspline_weights_f32<ORDER>(fy[u], wyf);
+                edf_bspline_weights_f32<ORDER>(fx[u], wxf);
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+                    const float* bi = b0 + i * slab;
+                    float ti = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const float* r = bi + j * EDF_SW_PITCH;
+                        float tj = r[0] * wxf[0];
+#pragma unroll
+                        for (int k = 1; k < NT; ++k) tj = fmaf(r[k], wxf[k], tj);
+                        ti = (j == 0) ? tj * wyf[0] : fmaf(tj, wyf[j], ti);
+                    }
+                    acc = (i == 0) ? ti * wzf[0] : fmaf(ti, wzf[i], acc);
+                }
+                if (a) pout[obase_zx + (yc0 + u) * osy] = acc;
+            }
+        } else if (!empty) {
+            // the chunk's tap windows span more than the window holds (very steep field): straight from global memory
+#pragma unroll
+            for (int u = 0; u < EDF_SW_MR; ++u) {
+                if (!((actm >> u) & 1u)) continue;
+                const int stz = z - EDF_SW_PK_BIAS + (int)(pk[u] >> 20), sty = yc0 + u - EDF_SW_PK_BIAS + (int)((pk[u] >> 10) & 1023u);
+                const int stx = x - EDF_SW_PK_BIAS + (int)(pk[u] & 1023u);
+                pout[obase_zx + (yc0 + u) * osy] =
+                    edf_swin_direct_gather<ORDER>(pin, stz, sty, stx, fz[u], fy[u], fx[u], lenz, leny, lenx, isz, isy);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EDF_SW_MR; ++u)
+            if ((cstm >> u) & 1u) pout[obase_zx + (yc0 + u) * osy] = cvalf;            // deform.c:903
+        // ---- rare voxels (next to a rounding / boundary threshold, huge displacements, chunks that do not fit
+        //      the window): the single-voxel routine, from the same table coordinates.  The only call of the loop
+        //      body sits here, where no per-chunk state is live.
+        if (slowm) {
+#pragma unroll 1
+            for (int u = 0; u < EDF_SW_MR; ++u) {
+                if (!((slowm >> u) & 1u)) continue;
+                double inz, iny, inx;
+                edf_gw_coords(p, Bw, u, sxrel, wx, affine, z, yc0 + u, x, bz, bx, offy, inz, iny, inx);
+                edf_lean_forward_slow<ORDER>(p, L, ii, z, yc0 + u, x, inz, iny, inx, gate);
+            }
+        }
+        __syncwarp();                                              // lanes in the rare-voxel loop still read this chunk's Bw
+        par = par == 2 ? 0 : par + 1;
+    }
+}
+
+// =======================================================================================
+// Gradient scatter through the same window (K2): the adjoint of the kernel above.
+//
+// Same chunks, same coordinate phase and the same exact bounding box, but instead of being filled from
+// the volume the window starts out zero, every active voxel ADDS its (order+1)^3 contributions
+// dY * wz * wy * wx to it with native shared-memory integer atomics (32-bit fixed point: float atomics
+// are CAS loops on sm_100; the largest possible contribution of the chunk maps to just under 2^22, so
+// a cell holds 512 of them and the resolution is max|dY_chunk| * wmax^3 * 2^-22), and the box is then added to dX
+// once with 16-byte vector atomics (RED.128), row by row, and re-zeroed.  Against edf_lean3d_gradwin_kernel
+// (fixed 19x23x52 window): rows are 64 cells apart, so the ATOMS of a warp collide only where the field
+// stretches (2.8 -> ~1.6 wavefronts each); the box is exact, so no voxel misses the window and only the
+// box -- not the whole window -- is flushed; taps across the border of the volume accumulate in virtual
+// cells whose row / column is folded back by the reference's mirror map (deform.c:796-810) at flush time.
+// =======================================================================================
+template <int ORDER, bool CMODE>
+__global__ void __launch_bounds__(EDF_SW_THREADS, 2)
+edf_swin3d_grad_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    EdfSwinSmem& s = *reinterpret_cast<EdfSwinSmem*>(smem_raw);
+    constexpr int NT = ORDER + 1;
+    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;     // warp = slab
+    const int x0 = blockIdx.x * EDF_SW_TX;
+    const int ry = (int)L.rows_per_cta;
+    const int y0 = blockIdx.y * ry;
+    const int z0 = blockIdx.z * EDF_SW_G;
+    int* const win = reinterpret_cast<int*>(s.win);
+
+    // ---- prologue: control tables, z-contraction A, empty boxes, zero window
+    if (tid == 0) s.nonzero = 0;
+    if (tid < 3 * 8) (&s.bb[0][0])[tid] = ((tid & 7) < 3) ? INT_MAX : INT_MIN;
+    if (tid < EDF_SW_TX) {
+        edf_fast_ctrl_entry(p, 2, min((int64_t)(x0 + tid), p.odim[2] - 1), s.wx[tid], &s.sx[tid]);
+    } else if (tid < EDF_SW_TX + EDF_SW_RY) {
+        const int t = tid - EDF_SW_TX;
+        edf_fast_ctrl_entry(p, 1, min((int64_t)(y0 + t), p.odim[1] - 1), s.wy[t], &s.sy[t]);
+    } else if (tid < EDF_SW_TX + EDF_SW_RY + EDF_SW_G) {
+        const int t = tid - EDF_SW_TX - EDF_SW_RY;
+        edf_fast_ctrl_entry(p, 0, min((int64_t)(z0 + t), p.odim[0] - 1), s.wz[t], &s.sz[t]);
+    }
+    for (int e = tid; e < EDF_SW_ROWS * EDF_SW_PITCH / 4; e += EDF_SW_THREADS)
+        reinterpret_cast<int4*>(win)[e] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+    {
+        const int sy_min0 = s.sy[0], sx_min0 = s.sx[0];
+        const int ny = s.sy[EDF_SW_RY - 1] - sy_min0 + 4;
+        const int nxx = s.sx[EDF_SW_TX - 1] - sx_min0 + 4;
+        if (tid == 0) { s.ny = ny; s.nx = nxx; }
+        bool nz = false;
+        const int na = 3 * EDF_SW_G * ny * nxx;
+        for (int e = tid; e < na; e += EDF_SW_THREADS) {
+            const int jx = e % nxx;
+            const int jy = (e / nxx) % ny;
+            const int t = (e / (nxx * ny)) % EDF_SW_G;
+            const int h = e / (nxx * ny * EDF_SW_G);
+            const int my = edf_mirror_index32(sy_min0 + jy, (int)p.ncp[1]);
+            const int mx = edf_mirror_index32(sx_min0 + jx, (int)p.ncp[2]);
+            const char* base = p.disp + p.dstr[0] * h + my * p.dstr[2] + mx * p.dstr[3];
+            double a = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int mz = edf_mirror_index32(s.sz[t] + i, (int)p.ncp[0]);
+                const double cf = (p.ddtype == EDF_F64) ? *(const double*)(base + mz * p.dstr[1])
+                                                        : (double)*(const float*)(base + mz * p.dstr[1]);
+                nz |= (cf != 0.0);
+                a = fma(cf, s.wz[t][i], a);
+            }
+            s.A[h][t][jy][jx] = a;
+        }
+        if (nz) s.nonzero = 1;
+    }
+    __syncthreads();
+
+    const int x = x0 + lane, z = z0 + g;
+    const int odz = (int)p.odim[0], ody = (int)p.odim[1], odx = (int)p.odim[2];
+    const bool tok = (x < odx) && (z < odz);
+    double wx[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wx[k] = s.wx[lane][k];
+    const int sxrel = s.sx[lane] - s.sx[0];
+    const int nchunk = min(ry / EDF_SW_MR, (ody - y0 + EDF_SW_MR - 1) / EDF_SW_MR);
+    const bool gate = s.nonzero != 0;
+    const int nx = s.nx, sy_min = s.sy[0];
+    double (*Bw)[EDF_SW_MR][EDF_SW_NC] = s.Bw[g];
+
+    const EdfInputDesc& d = p.inp[ii];
+    float* __restrict__ pdx = (float*)d.in;                       // dX accumulator
+    const float* __restrict__ pdy = (const float*)d.out;          // upstream gradient dY
+    const int lenz = (int)p.idim[0], leny = (int)p.idim[1], lenx = (int)p.idim[2];
+    const double limz = p.idim_m1[0], limy = p.idim_m1[1], limx = p.idim_m1[2];
+    const int isz = L.istr_e[ii][0], isy = L.istr_e[ii][1];
+    const int osy = L.ostr_e[ii][1];
+    const int obase_zx = z * L.ostr_e[ii][0] + x * L.ostr_e[ii][2];
+    const bool affine = p.has_affine != 0;
+    const double bz = xadd((double)z, p.ooff_d[0]);
+    const double bx = xadd((double)x, p.ooff_d[2]);
+    const double offy = p.ooff_d[1];
+    const int sq = tid & 15, srow = tid >> 4;                     // flush role: 16 lanes per window row
+
+    // dY of the next chunk is loaded one chunk ahead (its latency hides behind the scatter / flush phases)
+    float gvn[EDF_SW_MR];
+#pragma unroll
+    for (int u = 0; u < EDF_SW_MR; ++u)
+        gvn[u] = (tok && nchunk > 0 && y0 + u < ody) ? __ldg(pdy + (obase_zx + (y0 + u) * osy)) : 0.f;
+
+    int par = 0;
+    for (int c = 0; c < nchunk; ++c) {
+        const int yc0 = y0 + c * EDF_SW_MR;
+        {
+            const int m = lane & 3, q = lane >> 2;
+            const int row = c * EDF_SW_MR + m;
+            const int r0 = s.sy[row] - sy_min;
+            double wyr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wyr[j] = s.wy[row][j];
+            int h = 0, jx = q;
+            while (jx >= nx) { jx -= nx; ++h; }
+            while (h < 3) {
+                double b = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b = fma(s.A[h][g][r0 + j][jx], wyr[j], b);
+                Bw[h][m][jx] = b;
+                jx += 8;
+                while (jx >= nx) { jx -= nx; ++h; }
+            }
+        }
+        __syncwarp();
+
+        // ---- phase A: dY, coordinates and classification of this thread's 4 voxels
+        unsigned pk[EDF_SW_MR];
+        float fz[EDF_SW_MR], fy[EDF_SW_MR], fx[EDF_SW_MR], gv[EDF_SW_MR];
+        unsigned actm = 0, slowm = 0, dirm = 0;
+        int mnz = INT_MAX, mny = INT_MAX, mnx = INT_MAX, mxz = INT_MIN, mxy = INT_MIN, mxx = INT_MIN;
+        float gmax = 0.f;
+#pragma unroll
+        for (int u = 0; u < EDF_SW_MR; ++u) {
+            const int y = yc0 + u;
+            const bool valid = tok && (y < ody);
+            gv[u] = gvn[u];                                       // 0 for voxels outside the output
+            const bool live = valid & (gv[u] != 0.f);             // zero gradients contribute nothing
+            int stz, sty, stx;
+            bool slow, cst, oob;
+            edf_swin_voxel<ORDER, CMODE>(p, d.mode, Bw, u, sxrel, wx, affine, z, y, x, bz, bx, offy, limz, limy, limx,
+                                         lenz, leny, lenx, gate, stz, sty, stx, fz[u], fy[u], fx[u], slow, cst, oob);
+            const bool packed = edf_swin_pack(stz - z, sty - y, stx - x, pk[u]);
+            slow = live & (slow | (!cst & !packed));
+            if (slow) slowm |= 1u << u;
+            // Voxels that a non-constant boundary mode folded back into the volume pile up on the border cells
+            // (all of a chunk's out-of-range voxels can land on ONE cell in 'nearest' mode), which the 32-bit
+            // fixed-point cells of the window cannot hold: they scatter straight to dX in float.
+            if (!CMODE && live & !slow & oob) dirm |= 1u << u;
+            else if (live & !slow & !cst) {                       // constant voxels pass no gradient (deform.c:928)
+                actm |= 1u << u;
+                mnz = min(mnz, stz); mny = min(mny, sty); mnx = min(mnx, stx);
+                mxz = max(mxz, stz); mxy = max(mxy, sty); mxx = max(mxx, stx);
+                gmax = fmaxf(gmax, fabsf(gv[u]));
+            }
+        }
+
+        // ---- phase B: exact bounding box of the chunk's tap windows, max |dY| of the active voxels
+        mnz = __reduce_min_sync(0xffffffffu, mnz);
+        mny = __reduce_min_sync(0xffffffffu, mny);
+        mnx = __reduce_min_sync(0xffffffffu, mnx);
+        mxz = __reduce_max_sync(0xffffffffu, mxz);
+        mxy = __reduce_max_sync(0xffffffffu, mxy);
+        mxx = __reduce_max_sync(0xffffffffu, mxx);
+        const int gbits = __reduce_max_sync(0xffffffffu, __float_as_int(gmax));    // non-negative floats order as ints
+        if (lane == 0 && mnz != INT_MAX) {
+            int* b = s.bb[par];
+            atomicMin(b + 0, mnz); atomicMin(b + 1, mny); atomicMin(b + 2, mnx);
+            atomicMax(b + 3, mxz); atomicMax(b + 4, mxy); atomicMax(b + 5, mxx);
+            atomicMax(b + 6, gbits);
+        }
+        __syncthreads();                                           // box complete; previous chunk's flush done
+        if (tid < 8) s.bb[par == 0 ? 2 : par - 1][tid] = (tid < 3) ? INT_MAX : INT_MIN;
+#pragma unroll
+        for (int u = 0; u < EDF_SW_MR; ++u) {
+            const int yn = yc0 + EDF_SW_MR + u;
+            gvn[u] = (tok && c + 1 < nchunk && yn < ody) ? __ldg(pdy + (obase_zx + yn * osy)) : 0.f;
+        }
+        const int wz0 = s.bb[par][0], wy0 = s.bb[par][1], wx0 = s.bb[par][2] & ~3;
+        const int nzw = s.bb[par][3] - wz0 + NT, nyw = s.bb[par][4] - wy0 + NT;
+        const int nq = ((s.bb[par][5] + NT - 1 - wx0) >> 2) + 1;
+        const bool empty = s.bb[par][0] > s.bb[par][3];
+        const bool fit = !empty && nq <= EDF_SW_MAXQ && nzw <= EDF_SW_ROWS && nyw <= EDF_SW_ROWS && nzw * nyw <= EDF_SW_ROWS &&
+                         !(L.input_mask >> 31);
+        if (fit) {
+            // fixed-point scale: the largest possible contribution, max|dY| of the chunk times the largest weight
+            // product of this order, maps to just under 2^22 -- the range of the magic-number rounding that
+            // orders >= 2 use (FFMA + IADD; F2I runs at a quarter of the rate) -- so a cell holds 512 such
+            // contributions; resolution max|dY_chunk| * wmax^3 * 2^-22 (7e-8 max|dY| at order 3).
+            const float gmax_c = __int_as_float(s.bb[par][6]);
+            constexpr float WMAX = (ORDER <= 1) ? 1.0f : (ORDER == 2) ? 0.75f : (ORDER == 3) ? (2.0f / 3.0f)
+                                 : (ORDER == 4) ? (115.0f / 192.0f) : 0.55f;
+            // (orders 0 / 1 convert with F2I and have no such range limit: 2^24, 128 contributions per cell)
+            const float scale = ((ORDER <= 1 ? 16777216.0f : 4194304.0f) * 0.999f) /
+                                (fmaxf(gmax_c, 1e-30f) * (WMAX * WMAX * WMAX));
+            const float inv_scale = 1.0f / scale;
+            // ---- phase C: scatter into the window
+            const int slab = nyw * EDF_SW_PITCH;
+            const int lin0 = ((z - EDF_SW_PK_BIAS - wz0) * nyw + (yc0 - EDF_SW_PK_BIAS - wy0)) * EDF_SW_PITCH +
+                             (x - EDF_SW_PK_BIAS - wx0);
+#pragma unroll
+            for (int u = 0; u < EDF_SW_MR; ++u) {
+                if (!((actm >> u) & 1u)) continue;
+                const int rz = (int)(pk[u] >> 20), ryw = (int)((pk[u] >> 10) & 1023u), rx = (int)(pk[u] & 1023u);
+                int* b0 = win + (lin0 + u * EDF_SW_PITCH + (rz * nyw + ryw) * EDF_SW_PITCH + rx);
+                float wzf[NT], wyf[NT], wxf[NT];
+                if (ORDER > 0) {
+                    edf_bspline_weights_f32<ORDER>(fz[u], wzf);
+                    edf_bspline_weights_f32<ORDER>(fy[u], wyf);
+                    edf_bspline_weights_f32<ORDER>(fx[u], wxf);
+                }
+                const float gs = gv[u] * scale;
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+                    const float gi = (ORDER > 0) ? gs * wzf[i] : gs;
+                    int* bi = b0 + i * slab;
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const float gj = (ORDER > 0) ? gi * wyf[j] : gi;
+                        int* r = bi + j * EDF_SW_PITCH;
+#pragma unroll
+                        for (int k = 0; k < NT; ++k) {
+                            if (ORDER >= 2)      atomicAdd(r + k, edf_gw_round(gj, wxf[k]));
+                            else if (ORDER == 1) atomicAdd(r + k, __float2int_rn(gj * wxf[k]));
+                            else                 atomicAdd(r + k, __float2int_rn(gj));
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- phase D: add the box to dX (each touched 16-byte group once) and re-zero it.  Rows / planes
+            //      outside the volume fold back through the mirror map, groups left / right of it element-wise.
+            if (sq < nq) {
+                // thread -> (row yr of every plane, 16-byte group sq); the planes are the inner loop
+                const int gx = wx0 + 4 * sq;
+                const int pstep = nyw * EDF_SW_PITCH / 4;                                  // int4 units between planes
+                const bool interior = (wz0 >= 0) & (wz0 + nzw <= lenz) & (wy0 >= 0) & (wy0 + nyw <= leny) &
+                                      (wx0 >= 0) & (wx0 + 4 * nq <= lenx);                 // CTA-uniform
+                const bool xin = (unsigned)gx < (unsigned)lenx;
+                for (int yr = srow; yr < nyw; yr += EDF_SW_THREADS / 16) {
+                    int4* src = reinterpret_cast<int4*>(win + (yr * EDF_SW_PITCH + 4 * sq));
+                    if (interior) {
+                        // the box lies inside the volume: no mirror map
+                        float* dst = pdx + (wz0 * isz + (wy0 + yr) * isy + gx);
+                        for (int zr = 0; zr < nzw; ++zr, src += pstep, dst += isz) {
+                            const int4 v = *src;
+                            if ((v.x | v.y | v.z | v.w) != 0) {
+                                *src = make_int4(0, 0, 0, 0);
+                                atomicAdd(reinterpret_cast<float4*>(dst),
+                                          make_float4((float)v.x * inv_scale, (float)v.y * inv_scale,
+                                                      (float)v.z * inv_scale, (float)v.w * inv_scale));
+                            }
+                        }
+                    } else {
+                        const int gy = edf_mirror1(wy0 + yr, leny);
+                        for (int zr = 0; zr < nzw; ++zr, src += pstep) {
+                            const int4 v = *src;
+                            if ((v.x | v.y | v.z | v.w) != 0) {
+                                *src = make_int4(0, 0, 0, 0);
+                                float* dst = pdx + (edf_mirror1(wz0 + zr, lenz) * isz + gy * isy);
+                                const float4 f = make_float4((float)v.x * inv_scale, (float)v.y * inv_scale,
+                                                             (float)v.z * inv_scale, (float)v.w * inv_scale);
+                                if (xin) {
+                                    atomicAdd(reinterpret_cast<float4*>(dst + gx), f);
+                                } else {
+                                    if (v.x) atomicAdd(dst + edf_mirror1(gx, lenx), f.x);
+                                    if (v.y) atomicAdd(dst + edf_mirror1(gx + 1, lenx), f.y);
+                                    if (v.z) atomicAdd(dst + edf_mirror1(gx + 2, lenx), f.z);
+                                    if (v.w) atomicAdd(dst + edf_mirror1(gx + 3, lenx), f.w);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        } else if (!empty) {
+            dirm |= actm;                                          // does not fit the window (very steep field)
+        }
+        // ---- voxels that bypass the window: direct global atomics in float
+        if (dirm) {
+#pragma unroll
+            for (int u = 0; u < EDF_SW_MR; ++u) {
+                if (!((dirm >> u) & 1u)) continue;
+                const int stz = z - EDF_SW_PK_BIAS + (int)(pk[u] >> 20), sty = yc0 + u - EDF_SW_PK_BIAS + (int)((pk[u] >> 10) & 1023u);
+                const int stx = x - EDF_SW_PK_BIAS + (int)(pk[u] & 1023u);
+                edf_swin_direct_scatter<ORDER>(pdx, gv[u], stz, sty, stx, fz[u], fy[u], fx[u], lenz, leny, lenx, isz, isy);
+            }
+        }
+        // ---- rare voxels: the single-voxel routine (reference-order coordinates, global atomics)
+        if (slowm) {
+#pragma unroll 1
+            for (int u = 0; u < EDF_SW_MR; ++u) {
+                if (!((slowm >> u) & 1u)) continue;
+                double inz, iny, inx;
+                edf_gw_coords(p, Bw, u, sxrel, wx, affine, z, yc0 + u, x, bz, bx, offy, inz, iny, inx);
+                edf_gradwin_slow_voxel<ORDER>(p, L, ii, z, yc0 + u, x, inz, iny, inx, gate);
+            }
+        }
+        __syncwarp();                                              // lanes in the rare-voxel loop still read this chunk's Bw
+        par = par == 2 ? 0 : par + 1;
+    }
+}
+
+static bool g_swin_configured = false;
+
+// shared conditions of the two staged-window kernels
+static bool edf_swin_common_ok(const EdfParams& p, const EdfFastLaunch& L, int ii)
+{
+    if (!edf_lean_eligible(p, L, ii)) return false;
+    const EdfInputDesc& d = p.inp[ii];
+    if (d.mode == EDF_MODE_WRAP) return false;         // wrapped voxels land on the far side: no compact box
+    if (p.idim[2] % 4) return false;                   // 16-byte groups are inside or outside the volume as a whole
+    if (((uintptr_t)d.in % 16) || (L.istr_e[ii][0] % 4) || (L.istr_e[ii][1] % 4)) return false;
+    if (!edf_fast_ctrl_span_ok(p, 2, EDF_SW_TX, EDF_SW_NC)) return false;
+    if (!edf_fast_ctrl_span_ok(p, 1, EDF_SW_RY, EDF_SW_NC)) return false;
+    return true;
+}
+
+// forward: opt-in (EDF_FLAG_STAGED_FWD); measured slower than the direct gather on B200
+static bool edf_swin_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii)
+{
+    const EdfInputDesc& d = p.inp[ii];
+    if (d.order < 2 || d.order > 5) return false;
+    return edf_swin_common_ok(p, L, ii);
+}
+
+static int edf_swin_max_grad_order()
+{
+    static int v = -2;                                  // EDF_SWIN_GRAD_MAXORDER=-1 disables the kernel (A/B runs)
+    if (v < -1) { const char* e = getenv("EDF_SWIN_GRAD_MAXORDER"); v = (e && *e) ? atoi(e) : EDF_SWIN_GRAD_MAXORDER; }
+    return v;
+}
+
+static bool edf_swin_grad_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii, bool all_orders)
+{
+    const EdfInputDesc& d = p.inp[ii];
+    if (d.order < 0 || d.order > (all_orders ? 5 : edf_swin_max_grad_order())) return false;
+    return edf_swin_common_ok(p, L, ii);
+}
+
+static bool edf_swin_grid(const EdfParams& p, dim3& grid, unsigned& ry)
+{
+    grid.x = (unsigned)((p.odim[2] + EDF_SW_TX - 1) / EDF_SW_TX);
+    grid.z = (unsigned)((p.odim[0] + EDF_SW_G - 1) / EDF_SW_G);
+    ry = EDF_SW_RY;                                    // fewer rows per CTA for small volumes
+    while (ry > EDF_SW_MR && (uint64_t)grid.x * ((p.odim[1] + ry - 1) / ry) * grid.z < 4ull * 148) ry >>= 1;
+    grid.y = (unsigned)((p.odim[1] + ry - 1) / ry);
+    return grid.y <= 65535u && grid.z <= 65535u;
+}
+
+// returns 0 = launched, -2 = not applicable (caller takes the direct kernel), -1 = CUDA error
+static int edf_swin_launch(int order, int gradient, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& Lin, int ii)
+{
+    dim3 grid;
+    unsigned ry;
+    if (!edf_swin_grid(p, grid, ry)) return -2;
+    EdfFastLaunch L = Lin;
+    L.rows_per_cta = ry;
+    {
+        static int dbg = -1;                            // debug: EDF_SWIN_DEBUG_UNFIT=1 sends every chunk of the gradient
+        if (dbg < 0) { const char* e = getenv("EDF_SWIN_DEBUG_UNFIT"); dbg = (e && *e && *e != '0') ? 1 : 0; }   // kernel down
+        if (dbg) L.input_mask |= 0x80000000u;           // the "does not fit the window" path
+    }
+    const size_t smem = sizeof(EdfSwinSmem);
+    if (!g_swin_configured) {
+#define EDF_SW_ATTR(O)                                                                                              \
+    cudaFuncSetAttribute(edf_swin3d_fwd_kernel<O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    cudaFuncSetAttribute(edf_swin3d_fwd_kernel<O, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        EDF_SW_ATTR(2); EDF_SW_ATTR(3); EDF_SW_ATTR(4); EDF_SW_ATTR(5);
+#undef EDF_SW_ATTR
+#define EDF_SW_ATTR(O)                                                                                              \
+    cudaFuncSetAttribute(edf_swin3d_grad_kernel<O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    cudaFuncSetAttribute(edf_swin3d_grad_kernel<O, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        EDF_SW_ATTR(0); EDF_SW_ATTR(1); EDF_SW_ATTR(2); EDF_SW_ATTR(3); EDF_SW_ATTR(4); EDF_SW_ATTR(5);
+#undef EDF_SW_ATTR
+        if (cudaGetLastError() != cudaSuccess) return -1;
+        g_swin_configured = true;
+    }
+    const bool cm = p.inp[ii].mode == EDF_MODE_CONSTANT;
+#define EDF_SW_CASE(K, O)                                                                \
+    if (cm) K<O, true><<<grid, EDF_SW_THREADS, smem, st>>>(p, L, ii);                     \
+    else    K<O, false><<<grid, EDF_SW_THREADS, smem, st>>>(p, L, ii);                    \
+    break;
+    if (!gradient) {
+        switch (order) {
+        case 2: EDF_SW_CASE(edf_swin3d_fwd_kernel, 2)
+        case 3: EDF_SW_CASE(edf_swin3d_fwd_kernel, 3)
+        case 4: EDF_SW_CASE(edf_swin3d_fwd_kernel, 4)
+        default: EDF_SW_CASE(edf_swin3d_fwd_kernel, 5)
+        }
+    } else {
+        switch (order) {
+        case 0: EDF_SW_CASE(edf_swin3d_grad_kernel, 0)
+        case 1: EDF_SW_CASE(edf_swin3d_grad_kernel, 1)
+        case 2: EDF_SW_CASE(edf_swin3d_grad_kernel, 2)
+        case 3: EDF_SW_CASE(edf_swin3d_grad_kernel, 3)
+        case 4: EDF_SW_CASE(edf_swin3d_grad_kernel, 4)
+        default: EDF_SW_CASE(edf_swin3d_grad_kernel, 5)
+        }
+    }
+#undef EDF_SW_CASE
+    return 0;
+}
