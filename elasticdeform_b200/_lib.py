@@ -22,6 +22,7 @@ EDF_FLAG_NO_WINDOW = 2
 EDF_FLAG_STAGED_FWD = 4
 EDF_FLAG_FIXED_WINDOW = 8
 EDF_FLAG_STAGED_ALL = 16
+EDF_FLAG_STEEP = 32
 
 # numpy dtype -> edf_dtype (the 11 distinct element types of deform.c:863-888)
 _DTYPE_CODES = {

@@ -556,6 +556,8 @@ static void edf_lean_launch(int order, int gradient, dim3 grid, cudaStream_t st,
 static int edf_lean_launch_gradwin(int order, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii);
 static bool edf_gradwin_eligible(const EdfParams& p);
 static bool edf_swin_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii);
+static bool edf_swin_fwd_env();
+static int edf_swin_max_fwd_order();
 static bool edf_swin_grad_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii, bool all_orders);
 static int edf_swin_launch(int order, int gradient, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii);
 
@@ -601,12 +603,20 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
             L.rows_per_cta = ry;
             dim3 lgrid = grid;
             lgrid.y = (unsigned)((p.odim[AY] + ry - 1) / ry);
+            // staged-window kernels (edf_swin.cuh): forward at orders 2 / 3, gradient at orders 0-3, unless the
+            // caller hints a steep field (boxes that outgrow the window -> the round-1 kernels are faster there)
             int rcs = -2;
-            if (windows && !p.gradient && (flags & EDF_FLAG_STAGED_FWD) && edf_swin_eligible(p, L, ii))
-                rcs = edf_swin_launch(p.inp[ii].order, 0, st, p, L, ii);   // staged-window gather (edf_swin.cuh), opt-in
-            else if (windows && p.gradient && !(flags & EDF_FLAG_FIXED_WINDOW) &&
-                     edf_swin_grad_eligible(p, L, ii, (flags & EDF_FLAG_STAGED_ALL) != 0))
-                rcs = edf_swin_launch(p.inp[ii].order, 1, st, p, L, ii);   // staged-window scatter (edf_swin.cuh)
+            const bool steep = (flags & EDF_FLAG_STEEP) != 0;
+            const int ord = p.inp[ii].order;
+            if (windows && !p.gradient) {
+                const bool want = (flags & EDF_FLAG_STAGED_FWD) || edf_swin_fwd_env() ||
+                                  (!steep && ord >= 2 && ord <= edf_swin_max_fwd_order());
+                if (want && edf_swin_eligible(p, L, ii)) rcs = edf_swin_launch(ord, 0, st, p, L, ii);
+            } else if (windows && p.gradient && !(flags & EDF_FLAG_FIXED_WINDOW) &&
+                       ((flags & EDF_FLAG_STAGED_ALL) || !(steep && ord >= 2))) {
+                if (edf_swin_grad_eligible(p, L, ii, (flags & EDF_FLAG_STAGED_ALL) != 0))
+                    rcs = edf_swin_launch(ord, 1, st, p, L, ii);
+            }
             if (rcs == -1) return -1;
             if (rcs == 0) {
                 *name = p.gradient ? "swin3d_f32_grad" : "swin3d_f32";

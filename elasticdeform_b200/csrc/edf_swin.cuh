@@ -58,6 +58,7 @@ struct EdfSwinSmem {
     int    sx[EDF_SW_TX];
     int    ny, nx, nonzero, pad_;
     int    bb[3][8];                // [chunk % 3]: min z,y,x start, max z,y,x start of the chunk's active voxels
+    unsigned long long mbar;        // transaction barrier of the TMA bulk copies that fill the window
     double A[3][EDF_SW_G][EDF_SW_NC][EDF_SW_NC];
     double Bw[EDF_SW_G][3][EDF_SW_MR][EDF_SW_NC];
     __align__(128) float win[EDF_SW_ROWS * EDF_SW_PITCH];
@@ -70,6 +71,41 @@ __device__ __forceinline__ void edf_cp_async16(uint32_t smem_dst, const float* g
 __device__ __forceinline__ void edf_cp_async4(uint32_t smem_dst, const float* gsrc)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+// ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP): one instruction moves a whole window row global -> shared and
+//      reports its bytes to a transaction mbarrier.  (The tensor-map forms of TMA trap on this pool's B200 boxes,
+//      see DESIGN.md; the row form needs no descriptor and suits the data-dependent box anyway.)
+#ifndef EDF_SW_BULK
+#define EDF_SW_BULK 1              // 1: stage the window with TMA bulk copies; 0: with 16-byte cp.async (LDGSTS)
+#endif
+__device__ __forceinline__ void edf_mbar_init(unsigned long long* mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void edf_mbar_expect_tx(unsigned long long* mbar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void edf_mbar_wait(unsigned long long* mbar, unsigned phase)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "EDF_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra EDF_MBAR_DONE_%=;\n"
+        "bra EDF_MBAR_WAIT_%=;\n"
+        "EDF_MBAR_DONE_%=:\n"
+        "}\n" :: "r"(a), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void edf_bulk_g2s(uint32_t smem_dst, const float* gsrc, unsigned bytes, unsigned long long* mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_dst), "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(mbar)) : "memory");
 }
 
 // exact floor / window start / fractional offset without conversion instructions for the floor:
@@ -232,7 +268,10 @@ edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
     const int z0 = blockIdx.z * EDF_SW_G;
 
     // ---- prologue: control tables, z-contraction A of the displacement coefficients, empty boxes
-    if (tid == 0) s.nonzero = 0;
+    if (tid == 0) {
+        s.nonzero = 0;
+        if (EDF_SW_BULK) edf_mbar_init(&s.mbar, 1);
+    }
     if (tid < 3 * 8) (&s.bb[0][0])[tid] = ((tid & 7) < 3) ? INT_MAX : INT_MIN;
     if (tid < EDF_SW_TX) {
         edf_fast_ctrl_entry(p, 2, min((int64_t)(x0 + tid), p.odim[2] - 1), s.wx[tid], &s.sx[tid]);
@@ -304,6 +343,7 @@ edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
     const int sq = tid & 15, srow = tid >> 4;
 
     int par = 0;                                                   // c % 3
+    unsigned mphase = 0;                                           // parity of the window barrier's current phase
     for (int c = 0; c < nchunk; ++c) {
         const int yc0 = y0 + c * EDF_SW_MR;
         // ---- warp-private y-contraction for the 4 rows of the chunk (lane -> row m, phase q)
@@ -377,6 +417,49 @@ edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
             //      the reference's edge taps read (deform.c:796-810); 16-byte groups left or right of the volume
             //      (lenx % 4 == 0: inside or outside as a whole) likewise, element by element.
             const int rows = nzw * nyw;
+#if EDF_SW_BULK
+            {
+                // one bulk copy per window row (the part of it inside the volume along x), issued by one thread
+                // each; thread 0 announces the byte total to the transaction barrier, every thread then waits
+                // for the phase to complete.  Groups left / right of the volume: element-wise, mirrored.
+                const int xs = max(wx0, 0), xe = min(wx0 + 4 * nq, lenx);
+                const unsigned rbytes = (unsigned)(xe - xs) * 4u;
+                if (tid == 0) edf_mbar_expect_tx(&s.mbar, rbytes * (unsigned)rows);
+                const unsigned inv_y = 0xffffffffu / (unsigned)nyw + 1u;                    // nyw >= 3
+                for (int r = tid; r < rows; r += EDF_SW_THREADS) {
+                    const int zr = (int)__umulhi((unsigned)r, inv_y);
+                    const int yr = r - zr * nyw;
+                    const int gz = edf_mirror1(wz0 + zr, lenz), gy = edf_mirror1(wy0 + yr, leny);
+                    edf_bulk_g2s(win_s + (uint32_t)(r * EDF_SW_PITCH + (xs - wx0)) * 4u, pin + (gz * isz + gy * isy + xs), rbytes, &s.mbar);
+                }
+                const bool xborder = (wx0 < 0) | (wx0 + 4 * nq > lenx);                     // CTA-uniform
+                if (xborder) {
+                    // at most one group on either side (the window reaches at most `order` cells past the border)
+                    const int side = tid & 1;                                              // 0: left group, 1: right group
+                    const int gx = side ? lenx : -4;
+                    const bool need = side ? (wx0 + 4 * nq > lenx) : (wx0 < 0);
+                    if (need) {
+                        const int m0 = edf_mirror1(gx, lenx), m1 = edf_mirror1(gx + 1, lenx);
+                        const int m2 = edf_mirror1(gx + 2, lenx), m3 = edf_mirror1(gx + 3, lenx);
+                        for (int r = tid >> 1; r < rows; r += EDF_SW_THREADS / 2) {
+                            const int zr = (int)__umulhi((unsigned)r, inv_y);
+                            const int yr = r - zr * nyw;
+                            const float* src = pin + (edf_mirror1(wz0 + zr, lenz) * isz + edf_mirror1(wy0 + yr, leny) * isy);
+                            const uint32_t dst = win_s + (uint32_t)(r * EDF_SW_PITCH + (gx - wx0)) * 4u;
+                            edf_cp_async4(dst, src + m0);
+                            edf_cp_async4(dst + 4, src + m1);
+                            edf_cp_async4(dst + 8, src + m2);
+                            edf_cp_async4(dst + 12, src + m3);
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncthreads();
+                }
+                edf_mbar_wait(&s.mbar, mphase);
+                mphase ^= 1u;
+            }
+#else
             if (sq < nq) {
                 const int gx = wx0 + 4 * sq;
                 const bool xin = (unsigned)gx < (unsigned)lenx;
@@ -412,6 +495,7 @@ edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
+#endif
             // ---- phase D: gather from the window (inactive lanes read cell 0 and discard)
             const int slab = nyw * EDF_SW_PITCH;
             const int lin0 = ((z - EDF_SW_PK_BIAS - wz0) * nyw + (yc0 - EDF_SW_PK_BIAS - wy0)) * EDF_SW_PITCH +
@@ -795,7 +879,24 @@ static bool edf_swin_common_ok(const EdfParams& p, const EdfFastLaunch& L, int i
     return true;
 }
 
-// forward: opt-in (EDF_FLAG_STAGED_FWD); measured slower than the direct gather on B200
+static bool edf_swin_fwd_env()                          // EDF_STAGED_FWD=1: staged forward gather for every eligible call (A/B runs)
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("EDF_STAGED_FWD"); v = (e && *e && *e != '0') ? 1 : 0; }
+    return v != 0;
+}
+
+#ifndef EDF_SWIN_FWD_MAXORDER
+#define EDF_SWIN_FWD_MAXORDER 3       // staged forward gather by default at orders 2 .. this (B200, 256^3, sigma 8:
+#endif                                //   0.36 / 0.54 ms at orders 2 / 3 against 0.37 / 0.66 ms direct; slower at order 5)
+static int edf_swin_max_fwd_order()
+{
+    static int v = -2;                                  // EDF_SWIN_FWD_MAXORDER=-1: direct gather everywhere (A/B runs)
+    if (v < -1) { const char* e = getenv("EDF_SWIN_FWD_MAXORDER"); v = (e && *e) ? atoi(e) : EDF_SWIN_FWD_MAXORDER; }
+    return v;
+}
+
+// forward: orders 2-5 are implemented; which of them take this kernel by default is decided in edf_fast_try_launch
 static bool edf_swin_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii)
 {
     const EdfInputDesc& d = p.inp[ii];

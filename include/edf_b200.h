@@ -102,9 +102,11 @@ typedef struct {
 /* flags */
 #define EDF_FLAG_FORCE_GENERIC 1u     /* debug: never take a specialised kernel */
 #define EDF_FLAG_NO_WINDOW     2u     /* debug: direct gather / scatter kernels, no shared-memory window */
-#define EDF_FLAG_STAGED_FWD    4u     /* experiment: forward gather through a staged shared-memory window */
+#define EDF_FLAG_STAGED_FWD    4u     /* debug: staged-window forward gather at every eligible order (2..5) */
 #define EDF_FLAG_FIXED_WINDOW  8u     /* gradient through the fixed-size window kernel (better for very steep fields) */
 #define EDF_FLAG_STAGED_ALL    16u    /* debug: staged-window gradient kernel at every spline order */
+#define EDF_FLAG_STEEP         32u    /* hint: steep displacement field (rms gradient > ~0.25 voxel/voxel): the tap boxes
+                                         of a chunk outgrow the staged window, prefer the direct / fixed-window kernels */
 
 int edf_deform_grid(const edf_problem* problem, void* stream);
 int edf_deform_grid_grad(const edf_problem* problem, void* stream);

@@ -14,6 +14,10 @@ tail -2 gpurun_out/bench_$TAG.err; cat gpurun_out/bench_$TAG.json
 (timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv \
    --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 5 --warmup 3 > gpurun_out/bench_under_ncu_$TAG.log 2>&1; echo "ncu-list rc=$?")
 # full capture of the forward gather and the gradient scatter (one launch each)
-(timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:edf_(lean3d|fast_f32)' -s 4 -c 2 \
+(timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:edf_(swin3d|lean3d|fast_f32)' -s 4 -c 2 \
    -f -o gpurun_out/prof_$TAG python bench.py --steps 3 --warmup 3 > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu-full rc=$?")
+# two full captures exceed the 64 MiB return limit: export the pages that are read afterwards, drop the report
+ncu -i gpurun_out/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null
+ncu -i gpurun_out/prof_$TAG.ncu-rep --page source --csv > gpurun_out/prof_${TAG}_src.csv 2>/dev/null
+rm -f gpurun_out/prof_$TAG.ncu-rep
 ls -la gpurun_out | tail -12

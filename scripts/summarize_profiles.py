@@ -41,8 +41,12 @@ if os.path.exists(launches):
             f.write("| `%s` | %d | %.1f | %.1f %% |\n" % (k[:110], len(v), sum(v) / len(v) / 1e3, 100 * sum(v) / total))
     print("wrote", os.path.join(out_dir, "%s_launches.md" % tag))
 
-if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw_csv = os.path.join(ROOT, "gpurun_out", "prof_%s_raw.csv" % tag)     # exported on the GPU box (the .ncu-rep of two
+if os.path.exists(rep) or os.path.exists(raw_csv):                       # kernels exceeds gpurun's 64 MiB return limit)
+    if os.path.exists(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
+        raw = open(raw_csv).read()
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     keys = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -56,7 +60,14 @@ if os.path.exists(rep):
             "smsp__inst_executed.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
             "sass__inst_executed_global_loads", "smsp__inst_executed_op_global_red.sum",
             "smsp__inst_executed_op_shared_atom.sum", "sass__inst_executed_shared_loads",
-            "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.max"]
+            "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.max",
+            "sm__cycles_active.avg", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum",
+            "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+            "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio"]
     out = []
     for r in rows[2:]:
         d = {}
@@ -78,7 +89,12 @@ if os.path.exists(rep):
         t = to_bytes(d["dram__bytes_read.sum"]) + to_bytes(d["dram__bytes_write.sum"])
         n = d["Kernel Name"]
         if "edf_" in n:
-            key = "grad" if ("true" in n or ", 1>" in n or "grad" in n) else "fwd"
+            if "_fwd_" in n:
+                key = "fwd"
+            elif "grad" in n:
+                key = "grad"
+            else:
+                key = "grad" if ("true" in n or ", 1>" in n) else "fwd"
             traffic[key] = int(t)
     if traffic:
         traffic["source"] = "ncu --set full, %s" % tag
