@@ -333,8 +333,8 @@ def run_gpu_arm(args):
         dx = edf.deform_grid_gradient(Gn, D, order=ORDER, prefilter=False)
         return y, dx
 
-    for _ in range(2):
-        e2e_step()
+    for _ in range(3):                          # results held across the next call, as in the timed loop, so
+        y, dx = e2e_step()                      # that the pinned result pool reaches its steady-state size here
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):

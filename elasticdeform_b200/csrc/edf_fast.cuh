@@ -19,9 +19,20 @@
 #define EDF_FAST_RY 64             // rows (second-last axis) a CTA walks through, chunk by chunk
 #define EDF_FAST_THREADS (EDF_FAST_TX * EDF_FAST_G)
 
+// Tile schedule of the staged-window kernels (edf_swin.cuh): a 1-D grid whose CTAs are dispatched in
+// block-index order, cut into up to three segments of z-tiles with decreasing rows per CTA, so that
+// the CTAs that run last -- the tail during which SMs go idle one by one -- are short ones.
+struct EdfTileSched {
+    uint32_t nseg, gx;             // segments in use; tiles along x
+    uint32_t cta_begin[4];         // first block index of segment s (cta_begin[nseg] = grid size)
+    uint32_t z_begin[4];           // first z-tile of segment s
+    uint32_t ry[3], gy[3];         // rows per CTA and tiles along y of segment s
+};
+
 struct EdfFastLaunch {
     uint32_t input_mask;           // which p.inp[] entries this launch processes
     uint32_t rows_per_cta;         // lean kernels: rows of the second-last axis per CTA (multiple of 8, <= 64)
+    EdfTileSched sched;            // staged-window kernels only
     uint64_t cval_bits[EDF_MAX_INPUTS];   // constant value converted to the output dtype
     int32_t  istr_e[EDF_MAX_INPUTS][EDF_MAX_AXIS];   // element strides (deformed axes)
     int32_t  ostr_e[EDF_MAX_INPUTS][EDF_MAX_AXIS];

@@ -252,6 +252,21 @@ __device__ __forceinline__ void edf_swin_direct_scatter(float* __restrict__ pdx,
     }
 }
 
+// tile of this CTA from the 1-D block index (EdfTileSched)
+__device__ __forceinline__ void edf_swin_tile(const EdfTileSched& T, int& x0, int& y0, int& z0, int& ry)
+{
+    unsigned bid = blockIdx.x;
+    unsigned sgm = 0;
+    while (sgm + 1 < T.nseg && bid >= T.cta_begin[sgm + 1]) ++sgm;
+    bid -= T.cta_begin[sgm];
+    ry = (int)T.ry[sgm];
+    const unsigned tx = bid % T.gx, t = bid / T.gx;
+    const unsigned gy = T.gy[sgm];
+    x0 = (int)tx * EDF_SW_TX;
+    y0 = (int)(t % gy) * ry;
+    z0 = (int)(t / gy + T.z_begin[sgm]) * EDF_SW_G;
+}
+
 // CMODE: boundary mode 'constant' (out-of-range voxels take cval: no coordinate map, and no call inside
 // the coordinate phase, which keeps its register allocation free of call-crossing live ranges)
 template <int ORDER, bool CMODE>
@@ -262,10 +277,8 @@ edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
     EdfSwinSmem& s = *reinterpret_cast<EdfSwinSmem*>(smem_raw);
     constexpr int NT = ORDER + 1;
     const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;     // warp = slab
-    const int x0 = blockIdx.x * EDF_SW_TX;
-    const int ry = (int)L.rows_per_cta;
-    const int y0 = blockIdx.y * ry;
-    const int z0 = blockIdx.z * EDF_SW_G;
+    int x0, y0, z0, ry;
+    edf_swin_tile(L.sched, x0, y0, z0, ry);
 
     // ---- prologue: control tables, z-contraction A of the displacement coefficients, empty boxes
     if (tid == 0) {
@@ -285,7 +298,7 @@ edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
     __syncthreads();
     {
         const int sy_min0 = s.sy[0], sx_min0 = s.sx[0];
-        const int ny = s.sy[EDF_SW_RY - 1] - sy_min0 + 4;
+        const int ny = s.sy[ry - 1] - sy_min0 + 4;                  // control rows the CTA's ry rows touch
         const int nxx = s.sx[EDF_SW_TX - 1] - sx_min0 + 4;
         if (tid == 0) { s.ny = ny; s.nx = nxx; }
         bool nz = false;
@@ -581,10 +594,8 @@ edf_swin3d_grad_kernel(const __grid_constant__ EdfParams p, const __grid_constan
     EdfSwinSmem& s = *reinterpret_cast<EdfSwinSmem*>(smem_raw);
     constexpr int NT = ORDER + 1;
     const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;     // warp = slab
-    const int x0 = blockIdx.x * EDF_SW_TX;
-    const int ry = (int)L.rows_per_cta;
-    const int y0 = blockIdx.y * ry;
-    const int z0 = blockIdx.z * EDF_SW_G;
+    int x0, y0, z0, ry;
+    edf_swin_tile(L.sched, x0, y0, z0, ry);
     int* const win = reinterpret_cast<int*>(s.win);
 
     // ---- prologue: control tables, z-contraction A, empty boxes, zero window
@@ -604,7 +615,7 @@ edf_swin3d_grad_kernel(const __grid_constant__ EdfParams p, const __grid_constan
     __syncthreads();
     {
         const int sy_min0 = s.sy[0], sx_min0 = s.sx[0];
-        const int ny = s.sy[EDF_SW_RY - 1] - sy_min0 + 4;
+        const int ny = s.sy[ry - 1] - sy_min0 + 4;                  // control rows the CTA's ry rows touch
         const int nxx = s.sx[EDF_SW_TX - 1] - sx_min0 + 4;
         if (tid == 0) { s.ny = ny; s.nx = nxx; }
         bool nz = false;
@@ -918,24 +929,59 @@ static bool edf_swin_grad_eligible(const EdfParams& p, const EdfFastLaunch& L, i
     return edf_swin_common_ok(p, L, ii);
 }
 
-static bool edf_swin_grid(const EdfParams& p, dim3& grid, unsigned& ry)
+#ifndef EDF_SWIN_TAIL
+#define EDF_SWIN_TAIL 1            // 1: graded tail (the last z-tiles run with ry/2 and ry/4 rows per CTA); 0: uniform grid
+#endif
+static bool edf_swin_grid(const EdfParams& p, unsigned& ncta, EdfTileSched& T)
 {
-    grid.x = (unsigned)((p.odim[2] + EDF_SW_TX - 1) / EDF_SW_TX);
-    grid.z = (unsigned)((p.odim[0] + EDF_SW_G - 1) / EDF_SW_G);
-    ry = EDF_SW_RY;                                    // fewer rows per CTA for small volumes
-    while (ry > EDF_SW_MR && (uint64_t)grid.x * ((p.odim[1] + ry - 1) / ry) * grid.z < 4ull * 148) ry >>= 1;
-    grid.y = (unsigned)((p.odim[1] + ry - 1) / ry);
-    return grid.y <= 65535u && grid.z <= 65535u;
+    const uint64_t gx = (uint64_t)((p.odim[2] + EDF_SW_TX - 1) / EDF_SW_TX);
+    const uint64_t gz = (uint64_t)((p.odim[0] + EDF_SW_G - 1) / EDF_SW_G);
+    unsigned ry = EDF_SW_RY;                           // fewer rows per CTA for small volumes
+    static int env_ry = -1, env_tail = -2;              // EDF_SWIN_ROWS=4/8/16: rows per CTA; EDF_SWIN_TAIL=n: z-tiles in the
+    if (env_ry < 0) { const char* e = getenv("EDF_SWIN_ROWS"); env_ry = (e && *e) ? atoi(e) : 0; }     // graded tail, 0 = none
+    if (env_tail < -1) { const char* e = getenv("EDF_SWIN_TAIL"); env_tail = (e && *e) ? atoi(e) : -1; }  // (A/B runs)
+    if (env_ry == 4 || env_ry == 8 || env_ry == 16) ry = (unsigned)env_ry;
+    while (ry > EDF_SW_MR && gx * ((p.odim[1] + ry - 1) / ry) * gz < 4ull * 148) ry >>= 1;
+    const uint64_t per_z = gx * (uint64_t)((p.odim[1] + ry - 1) / ry);       // CTAs of one z-tile in the main segment
+    // graded tail: about one wave (2 CTAs on each of 148 SMs) of main-segment CTAs is replaced by CTAs of a
+    // half and a quarter of the rows, so that the last CTAs to finish are short.  Only for grids of several
+    // waves, and never more than a third of the volume.
+    uint64_t nt = 0;
+    if ((EDF_SWIN_TAIL || env_tail > 0) && env_tail != 0 && ry >= 2 * EDF_SW_MR && per_z * gz >= 3ull * 296) {
+        nt = env_tail > 0 ? (uint64_t)env_tail : (296 + per_z - 1) / per_z;
+        if (nt > gz / 3) nt = gz / 3;
+    }
+    const uint64_t nt2 = (ry >= 4 * EDF_SW_MR) ? nt / 2 : 0;                 // z-tiles at a quarter of the rows
+    const uint64_t nt1 = nt - nt2;                                           // z-tiles at half the rows
+    T.gx = (unsigned)gx;
+    uint64_t cta = 0, zt = 0;
+    unsigned sgm = 0;
+    const uint64_t zcount[3] = {gz - nt, nt1, nt2};
+    const unsigned rys[3] = {ry, ry / 2, ry / 4};
+    for (int k = 0; k < 3; ++k) {
+        if (!zcount[k]) continue;
+        const uint64_t gy = (uint64_t)((p.odim[1] + rys[k] - 1) / rys[k]);
+        T.cta_begin[sgm] = (unsigned)cta;
+        T.z_begin[sgm] = (unsigned)zt;
+        T.ry[sgm] = rys[k];
+        T.gy[sgm] = (unsigned)gy;
+        cta += gx * gy * zcount[k];
+        zt += zcount[k];
+        ++sgm;
+    }
+    T.nseg = sgm;
+    for (unsigned k = sgm; k < 4; ++k) { T.cta_begin[k] = (unsigned)cta; T.z_begin[k] = (unsigned)zt; }
+    ncta = (unsigned)cta;
+    return cta > 0 && cta < (1ull << 31);
 }
 
 // returns 0 = launched, -2 = not applicable (caller takes the direct kernel), -1 = CUDA error
 static int edf_swin_launch(int order, int gradient, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& Lin, int ii)
 {
-    dim3 grid;
-    unsigned ry;
-    if (!edf_swin_grid(p, grid, ry)) return -2;
     EdfFastLaunch L = Lin;
-    L.rows_per_cta = ry;
+    unsigned grid;
+    if (!edf_swin_grid(p, grid, L.sched)) return -2;
+    L.rows_per_cta = L.sched.ry[0];
     {
         static int dbg = -1;                            // debug: EDF_SWIN_DEBUG_UNFIT=1 sends every chunk of the gradient
         if (dbg < 0) { const char* e = getenv("EDF_SWIN_DEBUG_UNFIT"); dbg = (e && *e && *e != '0') ? 1 : 0; }   // kernel down

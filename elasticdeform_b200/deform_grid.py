@@ -14,6 +14,7 @@ Inputs may be NumPy arrays (copied to the GPU and back, like any accelerator
 plug-in) or torch CUDA tensors (zero copies; the result stays on the device).
 PyTorch is used only for device memory, streams and copies.
 """
+import collections
 import ctypes
 import threading
 import warnings
@@ -21,6 +22,7 @@ import warnings
 import numpy
 
 from . import _lib
+from . import _reach
 
 try:  # torch is plumbing (device memory / streams); required for any compute
     import torch
@@ -197,14 +199,6 @@ def _pipeline_plan(Xs, axis, order, mode, prefilter, inverse_affine, in_dim0, ou
     return -(-max(in_dim0, out_dim0) // _PIPELINE_SLABS)
 
 
-def _reach(displacement_f, order):
-    """Upper bound of |source index - (output index + offset)| along axis 0, taps included."""
-    dmax = float(displacement_f[0].abs().max().item())
-    if not numpy.isfinite(dmax):
-        return None
-    return int(numpy.ceil(dmax)) + int(max(order)) + 2
-
-
 _STEEP_RMS = 0.25
 
 
@@ -307,19 +301,88 @@ def _pinned_result(shape, torch_dtype):
     return block.view(torch_dtype).view(shape), arr
 
 
-def _pipelined_forward(lib, device, Xs, displacement_f, output_shapes, output_offset, axis, order, mode, cval,
+_SIDE_STREAMS = {}
+
+
+def _side_streams(device):
+    """The upload / download streams of the slab pipeline, one pair per device (creating a stream per
+    call costs more than the enqueue of a slab)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    pair = _SIDE_STREAMS.get(key)
+    if pair is None:
+        pair = _SIDE_STREAMS[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+    return pair
+
+
+_TRACE = None                                  # scripts/e2e_timeline.py sets a list: (label, timing event) pairs
+
+
+def _mark(label, stream):
+    if _TRACE is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        _TRACE.append((label, e))
+
+
+_BOUNDS_CACHE = collections.OrderedDict()      # a forward call and its gradient share one displacement
+
+
+def _slab_reach(displacement_f, order, dim0, off0, slabs):
+    """Per output slab (a, b): integers (lo, hi) such that every input plane a voxel of the slab reads or
+    scatters to, taps included, lies in [o + off0 + lo, o + off0 + hi] (o = the voxel's output plane).
+    A proof, not an estimate: elasticdeform_b200/_reach.py.  None when the coefficients are not finite.
+    Synchronises the current stream (the coefficients of the first axis, a few hundred values, come back
+    to the host)."""
+    c0 = displacement_f[0].to('cpu', torch.float64).numpy()
+    key = (c0.tobytes(), c0.shape, int(dim0), int(off0), tuple(slabs))
+    b = _BOUNDS_CACHE.get(key)
+    if b is None:
+        b = _reach.slab_bounds(c0, dim0, off0, slabs)
+        if b is None:
+            return None
+        _BOUNDS_CACHE[key] = b
+        while len(_BOUNDS_CACHE) > 8:
+            _BOUNDS_CACHE.popitem(last=False)
+    pad = int(max(order)) + 2
+    return [(int(numpy.floor(lo)) - pad, int(numpy.ceil(hi)) + pad) for lo, hi in b]
+
+
+class _SlabLauncher(object):
+    """One edf_problem reused for every slab of a pipelined call: only the crop offset along axis 0
+    and the outputs' base pointer / extent change between launches (building the ctypes structures
+    anew costs more host time than the launch itself)."""
+
+    def __init__(self, lib, gradient, ins, outs, displacement_f, output_offset, axis, order, mode, cval, flags):
+        naxis = len(axis[0])
+        offs = [int(v) for v in output_offset] if output_offset is not None else [0] * naxis
+        self.pr, self.keep = _build_problem(ins, outs, displacement_f, offs, axis, order, mode, cval, None, flags)
+        self.fn = lib.edf_deform_grid_grad if gradient else lib.edf_deform_grid
+        self.off0 = offs[0]
+        self.base = [(t.data_ptr(), t.stride(0) * t.element_size()) for t in outs]
+        self.stream = _stream_ptr(ins[0].device)
+        self.ref = ctypes.byref(self.pr)
+
+    def launch(self, a, b):
+        pr = self.pr
+        pr.output_offset[0] = self.off0 + a
+        for i, (ptr, step) in enumerate(self.base):
+            o = pr.outputs[i]
+            o.data = ptr + a * step
+            o.shape[0] = b - a
+        _lib.check(self.fn(self.ref, self.stream))
+
+
+def _pipelined_forward(lib, device, Xs, displacement, output_shapes, output_offset, axis, order, mode, cval,
                        h, flags):
-    n = len(Xs)
     in0, out0 = Xs[0].shape[0], output_shapes[0][0]
     off0 = int(output_offset[0]) if output_offset is not None else 0
-    reach = _reach(displacement_f, order)
-    if reach is None:
-        return None
     cur = torch.cuda.current_stream(device)
-    s_up, s_down = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    s_up, s_down = _side_streams(device)
     X_h = [_host_tensor(x) for x in Xs]
     X_d = [torch.empty(x.shape, dtype=x.dtype, device=device) for x in X_h]
     Y_d = [torch.empty(tuple(os), dtype=x.dtype, device=device) for os, x in zip(output_shapes, X_h)]
+    # the uploads go first: everything the host does from here on hides behind them
+    _mark("start", cur)
     s_up.wait_stream(cur)
     n_in = -(-in0 // h)
     up_done = []
@@ -331,39 +394,45 @@ def _pipelined_forward(lib, device, Xs, displacement_f, output_shapes, output_of
             ev = torch.cuda.Event()
             ev.record(s_up)
             up_done.append(ev)
-    Y_hn = [_pinned_result(os, x.dtype) for os, x in zip(output_shapes, X_h)]   # while the uploads run
+            _mark("upload %d done" % j, s_up)
+    displacement_f = _prefilter_displacement(lib, displacement, device)
+    slabs = [(k * h, min(out0, (k + 1) * h)) for k in range(-(-out0 // h))]
+    reach = _slab_reach(displacement_f, order, in0, off0, slabs)
+    if reach is None:
+        cur.wait_stream(s_up)
+        return None
+    Y_hn = [_pinned_result(os, x.dtype) for os, x in zip(output_shapes, X_h)]
     Y_h = [p[0] for p in Y_hn]
-    for k in range(-(-out0 // h)):
-        a, b = k * h, min(out0, (k + 1) * h)
-        need = min(in0 - 1, max(0, b - 1 + off0 + reach))
-        cur.wait_event(up_done[min(n_in - 1, need // h)])
-        offs = numpy.array([off0 + a] + ([int(v) for v in output_offset[1:]] if output_offset is not None
-                                          else [0] * (len(axis[0]) - 1)), dtype='int64')
-        _launch(lib, 0, X_d, [y[a:b] for y in Y_d], displacement_f, offs, axis, order, mode, cval, None, flags)
+    job = _SlabLauncher(lib, 0, X_d, Y_d, displacement_f, output_offset, axis, order, mode, cval, flags)
+    for (a, b), (_, hi) in zip(slabs, reach):
+        need = min(in0 - 1, max(0, b - 1 + off0 + hi))      # last input plane the slab can read
+        cur.wait_event(up_done[need // h])
+        _mark("kernel [%d,%d) after upload %d: start" % (a, b, need // h), cur)
+        job.launch(a, b)
+        _mark("kernel [%d,%d) done" % (a, b), cur)
         ev = torch.cuda.Event()
         ev.record(cur)
         s_down.wait_event(ev)
         with torch.cuda.stream(s_down):
             for yh, yd in zip(Y_h, Y_d):
                 yh[a:b].copy_(yd[a:b], non_blocking=True)
+            _mark("download [%d,%d) done" % (a, b), s_down)
     cur.wait_stream(s_down)
     cur.wait_stream(s_up)
+    _mark("end", cur)
     cur.synchronize()
     return [p[1] for p in Y_hn]
 
 
-def _pipelined_gradient(lib, device, dYs, X_shape, displacement_f, output_offset, axis, order, mode, cval,
+def _pipelined_gradient(lib, device, dYs, X_shape, displacement, output_offset, axis, order, mode, cval,
                         h, flags):
     in0, out0 = X_shape[0][0], dYs[0].shape[0]
     off0 = int(output_offset[0]) if output_offset is not None else 0
-    reach = _reach(displacement_f, order)
-    if reach is None:
-        return None
     cur = torch.cuda.current_stream(device)
-    s_up, s_down = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    s_up, s_down = _side_streams(device)
     G_h = [_host_tensor(g) for g in dYs]
     G_d = [torch.empty(g.shape, dtype=g.dtype, device=device) for g in G_h]
-    dX_d = [torch.zeros(tuple(sh), dtype=g.dtype, device=device) for sh, g in zip(X_shape, G_h)]
+    _mark("start", cur)
     s_up.wait_stream(cur)
     n_out = -(-out0 // h)
     up_done = []
@@ -375,35 +444,42 @@ def _pipelined_gradient(lib, device, dYs, X_shape, displacement_f, output_offset
             ev = torch.cuda.Event()
             ev.record(s_up)
             up_done.append(ev)
-    dX_hn = [_pinned_result(sh, g.dtype) for sh, g in zip(X_shape, G_h)]       # while the uploads run
+            _mark("upload %d done" % k, s_up)
+    dX_d = [torch.zeros(tuple(sh), dtype=g.dtype, device=device) for sh, g in zip(X_shape, G_h)]
+    displacement_f = _prefilter_displacement(lib, displacement, device)
+    slabs = [(k * h, min(out0, (k + 1) * h)) for k in range(n_out)]
+    reach = _slab_reach(displacement_f, order, in0, off0, slabs)
+    if reach is None:
+        cur.wait_stream(s_up)
+        return None
+    dX_hn = [_pinned_result(sh, g.dtype) for sh, g in zip(X_shape, G_h)]
     dX_h = [p[0] for p in dX_hn]
     n_in = -(-in0 // h)
+    # lowest input plane that output slabs k+1 .. can still scatter to: everything below is final after slab k
+    lowest = [in0] * (n_out + 1)
+    for k in range(n_out - 1, -1, -1):
+        lowest[k] = min(lowest[k + 1], slabs[k][0] + off0 + reach[k][0])
     flushed = 0                                             # dX slabs [0, flushed) are already on their way home
-
-    def flush_upto(j_end, ev):
-        nonlocal flushed
-        if j_end <= flushed:
-            return
-        s_down.wait_event(ev)
-        with torch.cuda.stream(s_down):
-            a, b = flushed * h, min(in0, j_end * h)
-            for xh, xd in zip(dX_h, dX_d):
-                xh[a:b].copy_(xd[a:b], non_blocking=True)
-        flushed = j_end
-
-    for k in range(n_out):
-        a, b = k * h, min(out0, (k + 1) * h)
+    job = _SlabLauncher(lib, 1, dX_d, G_d, displacement_f, output_offset, axis, order, mode, cval, flags)
+    for k, (a, b) in enumerate(slabs):
         cur.wait_event(up_done[k])
-        offs = numpy.array([off0 + a] + ([int(v) for v in output_offset[1:]] if output_offset is not None
-                                          else [0] * (len(axis[0]) - 1)), dtype='int64')
-        _launch(lib, 1, dX_d, [g[a:b] for g in G_d], displacement_f, offs, axis, order, mode, cval, None, flags)
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        # later output slabs start at b: they cannot reach input planes below b + off0 - reach
-        final_below = n_in if k == n_out - 1 else max(0, (b + off0 - reach) // h)
-        flush_upto(min(n_in, final_below), ev)
+        _mark("kernel [%d,%d): start" % (a, b), cur)
+        job.launch(a, b)
+        _mark("kernel [%d,%d) done" % (a, b), cur)
+        j_end = n_in if k == n_out - 1 else min(n_in, max(0, lowest[k + 1]) // h)
+        if j_end > flushed:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            s_down.wait_event(ev)
+            with torch.cuda.stream(s_down):
+                fa, fb = flushed * h, min(in0, j_end * h)
+                for xh, xd in zip(dX_h, dX_d):
+                    xh[fa:fb].copy_(xd[fa:fb], non_blocking=True)
+                _mark("download [%d,%d) done" % (fa, fb), s_down)
+            flushed = j_end
     cur.wait_stream(s_down)
     cur.wait_stream(s_up)
+    _mark("end", cur)
     cur.synchronize()
     return [p[1] for p in dX_hn]
 
@@ -525,8 +601,7 @@ def deform_grid(X, displacement, order=3, mode='constant', cval=0.0, crop=None, 
         if h is not None:
             for x in Xs:
                 _lib.dtype_code(x.dtype)
-            displacement_f = _prefilter_displacement(lib, displacement, device)
-            results = _pipelined_forward(lib, device, Xs, displacement_f, output_shapes, output_offset, axis,
+            results = _pipelined_forward(lib, device, Xs, displacement, output_shapes, output_offset, axis,
                                          order, mode, cval, h, _flags)
             if results is not None:
                 return results if isinstance(X, list) else results[0]
@@ -628,8 +703,7 @@ def deform_grid_gradient(dY, displacement, order=3, mode='constant', cval=0.0, c
         if h is not None:
             for dy in dYs:
                 _lib.dtype_code(dy.dtype)
-            displacement_f = _prefilter_displacement(lib, displacement, device)
-            results = _pipelined_gradient(lib, device, dYs, [tuple(sh) for sh in X_shape], displacement_f,
+            results = _pipelined_gradient(lib, device, dYs, [tuple(sh) for sh in X_shape], displacement,
                                           output_offset, axis, order, mode, cval, h, _flags)
             if results is not None:
                 return results if isinstance(dY, list) else results[0]
