@@ -932,22 +932,29 @@ static bool edf_swin_grad_eligible(const EdfParams& p, const EdfFastLaunch& L, i
 #ifndef EDF_SWIN_TAIL
 #define EDF_SWIN_TAIL 1            // 1: graded tail (the last z-tiles run with ry/2 and ry/4 rows per CTA); 0: uniform grid
 #endif
-static bool edf_swin_grid(const EdfParams& p, unsigned& ncta, EdfTileSched& T)
+// Measured on B200 (256^3 float32, 5^3 grid, CUDA events, same box; rows per CTA / graded tail):
+//   gradient, order 3, constant:   32 rows 0.778 ms | 16 rows 0.744 | 32 rows + tail 0.694   (orders 1 / 2: 1-4 % faster with the tail)
+//   forward,  order 3, constant:   32 rows 0.542 ms | 16 rows 0.516 | 32 rows + tail 0.566   (order 2: 32 rows best, 0.358 vs 0.376)
+//   forward / gradient, order 3, nearest (no cheap out-of-range CTAs at the end of the grid): the tail saves 9 % / 8-11 %
+// -> the gradient always takes the graded tail; the forward gather takes it in the non-constant modes, and in
+//    'constant' mode (where the last z-tiles are cheap anyway) runs 16 rows per CTA at orders >= 3.
+static bool edf_swin_grid(const EdfParams& p, int order, bool gradient, bool cmode, unsigned& ncta, EdfTileSched& T)
 {
     const uint64_t gx = (uint64_t)((p.odim[2] + EDF_SW_TX - 1) / EDF_SW_TX);
     const uint64_t gz = (uint64_t)((p.odim[0] + EDF_SW_G - 1) / EDF_SW_G);
-    unsigned ry = EDF_SW_RY;                           // fewer rows per CTA for small volumes
-    static int env_ry = -1, env_tail = -2;              // EDF_SWIN_ROWS=4/8/16: rows per CTA; EDF_SWIN_TAIL=n: z-tiles in the
+    unsigned ry = (!gradient && cmode && order >= 3) ? EDF_SW_RY / 2 : EDF_SW_RY;
+    const bool want_tail = gradient || !cmode;
+    static int env_ry = -1, env_tail = -2;              // EDF_SWIN_ROWS=4/8/16/32: rows per CTA; EDF_SWIN_TAIL=n: z-tiles in the
     if (env_ry < 0) { const char* e = getenv("EDF_SWIN_ROWS"); env_ry = (e && *e) ? atoi(e) : 0; }     // graded tail, 0 = none
     if (env_tail < -1) { const char* e = getenv("EDF_SWIN_TAIL"); env_tail = (e && *e) ? atoi(e) : -1; }  // (A/B runs)
-    if (env_ry == 4 || env_ry == 8 || env_ry == 16) ry = (unsigned)env_ry;
+    if (env_ry == 4 || env_ry == 8 || env_ry == 16 || env_ry == 32) ry = (unsigned)env_ry;
     while (ry > EDF_SW_MR && gx * ((p.odim[1] + ry - 1) / ry) * gz < 4ull * 148) ry >>= 1;
     const uint64_t per_z = gx * (uint64_t)((p.odim[1] + ry - 1) / ry);       // CTAs of one z-tile in the main segment
     // graded tail: about one wave (2 CTAs on each of 148 SMs) of main-segment CTAs is replaced by CTAs of a
     // half and a quarter of the rows, so that the last CTAs to finish are short.  Only for grids of several
     // waves, and never more than a third of the volume.
     uint64_t nt = 0;
-    if ((EDF_SWIN_TAIL || env_tail > 0) && env_tail != 0 && ry >= 2 * EDF_SW_MR && per_z * gz >= 3ull * 296) {
+    if (((EDF_SWIN_TAIL && want_tail) || env_tail > 0) && env_tail != 0 && ry >= 2 * EDF_SW_MR && per_z * gz >= 3ull * 296) {
         nt = env_tail > 0 ? (uint64_t)env_tail : (296 + per_z - 1) / per_z;
         if (nt > gz / 3) nt = gz / 3;
     }
@@ -980,7 +987,7 @@ static int edf_swin_launch(int order, int gradient, cudaStream_t st, const EdfPa
 {
     EdfFastLaunch L = Lin;
     unsigned grid;
-    if (!edf_swin_grid(p, grid, L.sched)) return -2;
+    if (!edf_swin_grid(p, order, gradient != 0, p.inp[ii].mode == EDF_MODE_CONSTANT, grid, L.sched)) return -2;
     L.rows_per_cta = L.sched.ry[0];
     {
         static int dbg = -1;                            // debug: EDF_SWIN_DEBUG_UNFIT=1 sends every chunk of the gradient
