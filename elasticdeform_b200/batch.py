@@ -88,3 +88,39 @@ def deform_grid_batch(Xs, displacements, order=3, mode='constant', cval=0.0, cro
                 res.append(_dg._from_device(dx, Xs[b]))
             return res
         return [_dg._from_device(o, x) for o, x in zip(outs, Xs)]
+
+
+def deform_random_grid_batch(Xs, sigma=25, points=3, order=3, mode='constant', cval=0.0, crop=None,
+                             prefilter=True, affines=None, generator=None, return_displacements=False):
+    """Batched twin of ``deform_random_grid`` (reference deform_grid.py:6-49): every volume of the batch
+    gets its own random displacement grid, sampled from N(0, sigma^2) at ``points`` control points per
+    axis, and the whole batch goes to the GPU in one ``edf_deform_grid_batch`` call.
+
+    ``generator``: None draws from NumPy's global RNG (``numpy.random.randn``, like the reference, one
+    draw per volume in batch order, so ``numpy.random.seed`` reproduces a Python loop over
+    ``deform_random_grid``); a ``torch.Generator`` of the CUDA device draws all grids on the device in one
+    call (no host round trip; the grids never leave the GPU).  ``return_displacements=True`` also
+    returns the grids that were used (a list of arrays / a CUDA tensor of shape (batch, naxis, P...)).
+    """
+    torch = _dg.torch
+    nb = len(Xs)
+    if nb == 0:
+        return ([], []) if return_displacements else []
+    ndim = Xs[0].ndim
+    if not isinstance(points, (list, tuple)):
+        points = [points] * ndim
+    assert len(points) == ndim, 'one number of control points per axis'
+    if generator is None:
+        Ds = [numpy.random.randn(ndim, *points) * sigma for _ in range(nb)]
+    else:
+        _dg._require_cuda()
+        dev = generator.device
+        assert dev.type == 'cuda', 'generator must be a CUDA generator (or None for the NumPy global RNG)'
+        Dt = torch.randn((nb, ndim) + tuple(int(q) for q in points), generator=generator, device=dev,
+                         dtype=torch.float64) * float(sigma)
+        Ds = [Dt[b] for b in range(nb)]
+    Ys = deform_grid_batch(Xs, Ds, order=order, mode=mode, cval=cval, crop=crop, prefilter=prefilter,
+                           affines=affines)
+    if return_displacements:
+        return Ys, (Ds if generator is None else Dt)
+    return Ys

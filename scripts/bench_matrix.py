@@ -100,7 +100,7 @@ def prefilter_times(shape=(256, 256, 256), order=3, reps=5):
 
 if __name__ == "__main__":
     S = (256, 256, 256)
-    for o in (0, 1, 3):
+    for o in (0, 1, 2, 3):
         run("256^3 f32 order %d" % o, [S], ['float32'], [o], (5, 5, 5), 8.0)
     run("256^3 f64 order 3 (fast_f64)", [S], ['float64'], [3], (5, 5, 5), 8.0, reps=10)
     run("cfg3 256^3 f32 o3 + int32 o0", [S, S], ['float32', 'int32'], [3, 0], (5, 5, 5), 8.0)
