@@ -121,7 +121,6 @@ edf_lean3d_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ E
 {
     __shared__ EdfLeanSmem s;
     constexpr int NT = ORDER + 1;
-    constexpr int NCHUNK = EDF_FAST_RY / EDF_FAST_M;
     const int x0 = blockIdx.x * EDF_FAST_TX;
     const int ry = (int)L.rows_per_cta;
     const int y0 = blockIdx.y * ry;
@@ -348,7 +347,6 @@ edf_lean3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
 {
     __shared__ EdfLeanSmem s;
     constexpr int NT = ORDER + 1;
-    constexpr int NCHUNK = EDF_FAST_RY / EDF_FAST_M;
     const int x0 = blockIdx.x * EDF_FAST_TX;
     const int ry = (int)L.rows_per_cta;
     const int y0 = blockIdx.y * ry;
@@ -718,7 +716,6 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
     extern __shared__ __align__(128) unsigned char smem_raw[];
     EdfGradWinSmem& s = *reinterpret_cast<EdfGradWinSmem*>(smem_raw);
     constexpr int NT = ORDER + 1;
-    constexpr int NCHUNK = EDF_FAST_RY / EDF_FAST_M;
     constexpr int NWIN = EDF_GW_WZ * EDF_GW_WY * EDF_GW_WX;
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * EDF_GW_TX;

@@ -392,15 +392,16 @@ edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
     const double bx = xadd((double)x, p.ooff_d[2]);
     const double offy = p.ooff_d[1];
     const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(s.win);
+#if !EDF_SW_BULK
     // staging role of this thread: 16 lanes per window row, one 16-byte group each
     const int sq = tid & 15, srow = tid >> 4;
+#endif
 
     int par = 0;                                                   // c % 3
     unsigned mphase = 0;                                           // parity of the window barrier's current phase
-    if (nchunk > 0) edf_swin_ycontract(s, Bw, g, lane, 0, nx, sy_min);
     for (int c = 0; c < nchunk; ++c) {
         const int yc0 = y0 + c * EDF_SW_MR;
-        // (the y-contraction Bw of this chunk was computed while the previous chunk's copies were in flight)
+        edf_swin_ycontract(s, Bw, g, lane, c, nx, sy_min);
         __syncwarp();
 
         // ---- phase A: coordinates and classification of this thread's 4 voxels (branch-free, two at a time)
@@ -492,6 +493,8 @@ edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                     __syncthreads();
                 }
+                edf_mbar_wait(&s.mbar, mphase);
+                mphase ^= 1u;
             }
 #else
             if (sq < nq) {
@@ -529,30 +532,6 @@ edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
-#endif
-        }
-        // ---- independent of the window, while the copies are in flight: constant voxels, the rare voxels, and the
-        //      next chunk's y-contraction
-#pragma unroll
-        for (int u = 0; u < EDF_SW_MR; ++u)
-            if ((cstm >> u) & 1u) pout[obase_zx + (yc0 + u) * osy] = cvalf;            // deform.c:903
-        // rare voxels (next to a rounding / boundary threshold, huge displacements): the single-voxel routine,
-        // from the same table coordinates
-        if (slowm) {
-#pragma unroll 1
-            for (int u = 0; u < EDF_SW_MR; ++u) {
-                if (!((slowm >> u) & 1u)) continue;
-                double inz, iny, inx;
-                edf_gw_coords(p, Bw, u, sxrel, wx, affine, z, yc0 + u, x, bz, bx, offy, inz, iny, inx);
-                edf_lean_forward_slow<ORDER>(p, L, ii, z, yc0 + u, x, inz, iny, inx, gate);
-            }
-        }
-        __syncwarp();                                              // lanes in the rare-voxel loop still read this chunk's Bw
-        if (c + 1 < nchunk) edf_swin_ycontract(s, Bw, g, lane, c + 1, nx, sy_min);
-        if (fit) {
-#if EDF_SW_BULK
-            edf_mbar_wait(&s.mbar, mphase);
-            mphase ^= 1u;
 #endif
             // ---- phase D: gather from the window (inactive lanes read cell 0 and discard)
             const int slab = nyw * EDF_SW_PITCH;
@@ -597,6 +576,25 @@ edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
                     edf_swin_direct_gather<ORDER>(pin, stz, sty, stx, fz[u], fy[u], fx[u], lenz, leny, lenx, isz, isy);
             }
         }
+#pragma unroll
+        for (int u = 0; u < EDF_SW_MR; ++u)
+            if ((cstm >> u) & 1u) pout[obase_zx + (yc0 + u) * osy] = cvalf;            // deform.c:903
+        // ---- rare voxels (next to a rounding / boundary threshold, huge displacements, chunks that do not fit
+        //      the window): the single-voxel routine, from the same table coordinates.  The only call of the loop
+        //      body sits here, where no per-chunk state is live.  (Moving this block, the constant stores and the
+        //      next chunk's y-contraction between the issue of the bulk copies and the wait for them -- to hide
+        //      the copy latency -- measured 5-12 % SLOWER, 0.518 vs 0.495 ms at order 3: the state kept live
+        //      across the call costs more than the wait.)
+        if (slowm) {
+#pragma unroll 1
+            for (int u = 0; u < EDF_SW_MR; ++u) {
+                if (!((slowm >> u) & 1u)) continue;
+                double inz, iny, inx;
+                edf_gw_coords(p, Bw, u, sxrel, wx, affine, z, yc0 + u, x, bz, bx, offy, inz, iny, inx);
+                edf_lean_forward_slow<ORDER>(p, L, ii, z, yc0 + u, x, inz, iny, inx, gate);
+            }
+        }
+        __syncwarp();                                              // lanes in the rare-voxel loop still read this chunk's Bw
         par = par == 2 ? 0 : par + 1;
     }
 }

@@ -173,8 +173,11 @@ def _launch(lib, gradient, ins, outs, displacement_f, output_offset, axis, order
 # = ~5 ms against a ~0.7 ms kernel.  PCIe is full duplex, so when the call allows it the volume is
 # cut into slabs along the first array axis and upload, kernel and download of different slabs
 # overlap on three streams.  What makes this legal is a rigorous bound on how far along that axis a
-# voxel can reach: the displacement is a convex combination of the (prefiltered) control-point
-# coefficients (B-spline weights are >= 0 and sum to 1), so |d_0| <= max|coefficient of axis 0|.
+# voxel can reach (_reach.py).  With prefilter=True and order > 1 the B-spline prefilter (forward) or its
+# adjoint (gradient) runs inside the pipeline in the reference's axis order: the pass along axis 0 needs
+# whole lines, i.e. the complete volume, the passes along the other axes work slab by slab, so the
+# download still overlaps them and the kernels.  Line filters are independent per line: the results
+# are bit-identical to the one-shot path.
 _PIPELINE_MIN_BYTES = 16 << 20
 _PIPELINE_SLABS = 8
 
@@ -187,8 +190,6 @@ def _pipeline_plan(Xs, axis, order, mode, prefilter, inverse_affine, in_dim0, ou
         return None
     for i, x in enumerate(Xs):
         if len(axis[i]) < 2 or axis[i][0] != 0:            # slabs must be slabs of the first DEFORMED axis
-            return None
-        if prefilter and order[i] > 1:                     # the prefilter recursion needs whole lines
             return None
         if int(mode[i]) not in (0, 4):                     # nearest / constant: coordinates are never folded
             return None                                    # back from far away (wrap, mirror, reflect are)
@@ -373,7 +374,8 @@ class _SlabLauncher(object):
 
 
 def _pipelined_forward(lib, device, Xs, displacement, output_shapes, output_offset, axis, order, mode, cval,
-                       h, flags):
+                       h, flags, prefilter=False):
+    pf = [int(order[i]) if (prefilter and order[i] > 1) else 0 for i in range(len(Xs))]
     in0, out0 = Xs[0].shape[0], output_shapes[0][0]
     off0 = int(output_offset[0]) if output_offset is not None else 0
     cur = torch.cuda.current_stream(device)
@@ -403,10 +405,28 @@ def _pipelined_forward(lib, device, Xs, displacement, output_shapes, output_offs
         return None
     Y_hn = [_pinned_result(os, x.dtype) for os, x in zip(output_shapes, X_h)]
     Y_h = [p[0] for p in Y_hn]
-    job = _SlabLauncher(lib, 0, X_d, Y_d, displacement_f, output_offset, axis, order, mode, cval, flags)
+    F_d = X_d
+    filtered = n_in                                         # input slabs [0, filtered) are fully prefiltered
+    if any(pf):
+        # prefilter (ref:155-164): the pass along axis 0 over the whole volume once it has arrived ...
+        cur.wait_event(up_done[-1])
+        F_d = [torch.empty_like(xd) if o else xd for xd, o in zip(X_d, pf)]
+        for xd, fd, o in zip(X_d, F_d, pf):
+            if o:
+                _spline_filter1d_device(lib, xd, fd, 0, o)
+        _mark("prefilter along axis 0 done", cur)
+        filtered = 0
+    job = _SlabLauncher(lib, 0, F_d, Y_d, displacement_f, output_offset, axis, order, mode, cval, flags)
     for (a, b), (_, hi) in zip(slabs, reach):
         need = min(in0 - 1, max(0, b - 1 + off0 + hi))      # last input plane the slab can read
         cur.wait_event(up_done[need // h])
+        while filtered <= need // h:                        # ... the other passes slab by slab, in place
+            fa, fb = filtered * h, min(in0, (filtered + 1) * h)
+            for i, (fd, o) in enumerate(zip(F_d, pf)):
+                for d in axis[i][1:]:
+                    if o:
+                        _spline_filter1d_device(lib, fd[fa:fb], fd[fa:fb], d, o)
+            filtered += 1
         _mark("kernel [%d,%d) after upload %d: start" % (a, b, need // h), cur)
         job.launch(a, b)
         _mark("kernel [%d,%d) done" % (a, b), cur)
@@ -425,7 +445,8 @@ def _pipelined_forward(lib, device, Xs, displacement, output_shapes, output_offs
 
 
 def _pipelined_gradient(lib, device, dYs, X_shape, displacement, output_offset, axis, order, mode, cval,
-                        h, flags):
+                        h, flags, prefilter=False):
+    pf = [int(order[i]) if (prefilter and order[i] > 1) else 0 for i in range(len(dYs))]
     in0, out0 = X_shape[0][0], dYs[0].shape[0]
     off0 = int(output_offset[0]) if output_offset is not None else 0
     cur = torch.cuda.current_stream(device)
@@ -467,6 +488,31 @@ def _pipelined_gradient(lib, device, dYs, X_shape, displacement, output_offset, 
         job.launch(a, b)
         _mark("kernel [%d,%d) done" % (a, b), cur)
         j_end = n_in if k == n_out - 1 else min(n_in, max(0, lowest[k + 1]) // h)
+        if any(pf):
+            # adjoint of the prefilter (ref:277-286): its pass along axis 0 needs the complete dX, the other
+            # passes and the download then go slab by slab
+            if k < n_out - 1:
+                continue
+            G_f = [torch.empty_like(xd) if o else xd for xd, o in zip(dX_d, pf)]
+            for xd, gf, o in zip(dX_d, G_f, pf):
+                if o:
+                    _spline_filter1d_device(lib, xd, gf, 0, o, adjoint=True)
+            _mark("prefilter adjoint along axis 0 done", cur)
+            for j in range(n_in):
+                fa, fb = j * h, min(in0, (j + 1) * h)
+                for i, (gf, o) in enumerate(zip(G_f, pf)):
+                    for d in axis[i][1:]:
+                        if o:
+                            _spline_filter1d_device(lib, gf[fa:fb], gf[fa:fb], d, o, adjoint=True)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                s_down.wait_event(ev)
+                with torch.cuda.stream(s_down):
+                    for xh, gf in zip(dX_h, G_f):
+                        xh[fa:fb].copy_(gf[fa:fb], non_blocking=True)
+                    _mark("download [%d,%d) done" % (fa, fb), s_down)
+            flushed = n_in
+            continue
         if j_end > flushed:
             ev = torch.cuda.Event()
             ev.record(cur)
@@ -602,7 +648,7 @@ def deform_grid(X, displacement, order=3, mode='constant', cval=0.0, crop=None, 
             for x in Xs:
                 _lib.dtype_code(x.dtype)
             results = _pipelined_forward(lib, device, Xs, displacement, output_shapes, output_offset, axis,
-                                         order, mode, cval, h, _flags)
+                                         order, mode, cval, h, _flags, prefilter)
             if results is not None:
                 return results if isinstance(X, list) else results[0]
 
@@ -704,7 +750,7 @@ def deform_grid_gradient(dY, displacement, order=3, mode='constant', cval=0.0, c
             for dy in dYs:
                 _lib.dtype_code(dy.dtype)
             results = _pipelined_gradient(lib, device, dYs, [tuple(sh) for sh in X_shape], displacement,
-                                          output_offset, axis, order, mode, cval, h, _flags)
+                                          output_offset, axis, order, mode, cval, h, _flags, prefilter)
             if results is not None:
                 return results if isinstance(dY, list) else results[0]
 

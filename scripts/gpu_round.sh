@@ -20,4 +20,6 @@ tail -2 gpurun_out/bench_$TAG.err; cat gpurun_out/bench_$TAG.json
 ncu -i gpurun_out/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_$TAG.ncu-rep --page source --csv > gpurun_out/prof_${TAG}_src.csv 2>/dev/null
 rm -f gpurun_out/prof_$TAG.ncu-rep
+(timeout 600 python scripts/bench_matrix.py > gpurun_out/matrix_$TAG.jsonl 2> gpurun_out/matrix_$TAG.err; echo "matrix rc=$?")
+cut -c1-200 gpurun_out/matrix_$TAG.jsonl
 ls -la gpurun_out | tail -12
