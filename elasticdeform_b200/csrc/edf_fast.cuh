@@ -566,6 +566,9 @@ static void edf_lean_launch(int order, int gradient, dim3 grid, cudaStream_t st,
                             const EdfFastLaunch& L, int ii);
 static int edf_lean_launch_gradwin(int order, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii);
 static bool edf_gradwin_eligible(const EdfParams& p);
+#ifndef EDF_SWIN_FWD_MIN_VOXELS
+#define EDF_SWIN_FWD_MIN_VOXELS (3ull << 20)   // output voxels from which the staged-window forward gather is the default
+#endif
 static bool edf_swin_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii);
 static bool edf_swin_fwd_env();
 static int edf_swin_max_fwd_order();
@@ -620,8 +623,11 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
             const bool steep = (flags & EDF_FLAG_STEEP) != 0;
             const int ord = p.inp[ii].order;
             if (windows && !p.gradient) {
+                // (and unless the volume is small: below ~two waves of CTAs the per-CTA prologue and the two barriers
+                //  per chunk weigh more than the cheaper taps -- 128^3, order 3: 0.169 ms staged against 0.137 ms direct)
+                const bool big = (uint64_t)p.odim[0] * (uint64_t)p.odim[1] * (uint64_t)p.odim[2] >= EDF_SWIN_FWD_MIN_VOXELS;
                 const bool want = (flags & EDF_FLAG_STAGED_FWD) || edf_swin_fwd_env() ||
-                                  (!steep && ord >= 2 && ord <= edf_swin_max_fwd_order());
+                                  (!steep && big && ord >= 2 && ord <= edf_swin_max_fwd_order());
                 if (want && edf_swin_eligible(p, L, ii)) rcs = edf_swin_launch(ord, 0, st, p, L, ii);
             } else if (windows && p.gradient && !(flags & EDF_FLAG_FIXED_WINDOW) &&
                        ((flags & EDF_FLAG_STAGED_ALL) || !(steep && ord >= 2))) {
