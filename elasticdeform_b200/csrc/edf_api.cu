@@ -350,13 +350,13 @@ static int run_line_filter(const edf_array* input, const edf_array* output, int 
     const size_t smem = (size_t)(L * per_line);
     const int64_t blocks = (p.nlines + L - 1) / L;
     if (blocks > 0x7fffffffLL) return edf_fail(EDF_ERR_RUNTIME, "too many lines");
-    static thread_local int configured_smem = 0;
-    if ((int)smem > configured_smem) {
+    static EdfPerDeviceFlag configured;                 // the limit is raised to the device's maximum, once per device
+    if (!configured.test()) {
         if (cudaFuncSetAttribute(edf_line_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  max_smem) != cudaSuccess)
             return edf_fail(EDF_ERR_CUDA, "cudaFuncSetAttribute: %s",
                             cudaGetErrorString(cudaGetLastError()));
-        configured_smem = max_smem;
+        configured.set();
     }
     int threads = 256;
     edf_line_filter_kernel<<<(unsigned)blocks, threads, smem, st>>>(p);

@@ -11,8 +11,28 @@
 // fp32 (float32 data); label copies move raw bits.
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include "edf_core.h"
 #include "edf_fast_core.h"
+
+// "Configured on this device" flag for cudaFuncSetAttribute: function attributes are PER DEVICE, so a process
+// that drives several GPUs has to raise the dynamic shared-memory limit of a kernel on each of them.  test() /
+// set() refer to the calling thread's current device; two threads may both configure (harmless), none launches
+// before the attributes are in place.  Devices beyond 127 are configured on every launch.
+struct EdfPerDeviceFlag {
+    std::atomic<uint64_t> mask[2];
+    static int device() { int d = 0; return cudaGetDevice(&d) == cudaSuccess ? d : -1; }
+    bool test() const
+    {
+        const int d = device();
+        return d >= 0 && d < 128 && ((mask[d >> 6].load(std::memory_order_acquire) >> (d & 63)) & 1ull);
+    }
+    void set()
+    {
+        const int d = device();
+        if (d >= 0 && d < 128) mask[d >> 6].fetch_or(1ull << (d & 63), std::memory_order_release);
+    }
+};
 
 #define EDF_FAST_G 4               // thread groups (slabs in 3-D, row blocks in 2-D)
 #define EDF_FAST_M 8               // rows per group and chunk

@@ -1183,7 +1183,7 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
     }
 }
 
-static bool g_gradwin_configured = false;
+static EdfPerDeviceFlag g_gradwin_configured;
 
 // The window kernel uses 32-lane x tiles; its control-point tables must hold a 32-wide span, and
 // dX element offsets must fit 32 bits (already guaranteed by edf_fast_input_class).
@@ -1206,7 +1206,7 @@ static int edf_lean_launch_gradwin(int order, cudaStream_t st, const EdfParams& 
     EdfFastLaunch L = Lin;
     L.rows_per_cta = ry;
     const size_t smem = sizeof(EdfGradWinSmem);
-    if (!g_gradwin_configured) {
+    if (!g_gradwin_configured.test()) {
 #define EDF_GW_ATTR(O)                                                                                           \
     cudaFuncSetAttribute(edf_lean3d_gradwin_kernel<O, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     cudaFuncSetAttribute(edf_lean3d_gradwin_kernel<O, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -1214,7 +1214,7 @@ static int edf_lean_launch_gradwin(int order, cudaStream_t st, const EdfParams& 
         EDF_GW_ATTR(0); EDF_GW_ATTR(1); EDF_GW_ATTR(2); EDF_GW_ATTR(3); EDF_GW_ATTR(4); EDF_GW_ATTR(5);
 #undef EDF_GW_ATTR
         if (cudaGetLastError() != cudaSuccess) return -1;
-        g_gradwin_configured = true;
+        g_gradwin_configured.set();
     }
     // 16-byte vector flush / TMA need 16-byte aligned rows of dX
     const bool vec = ((uintptr_t)p.inp[ii].in % 16 == 0) && (L.istr_e[ii][0] % 4 == 0) && (L.istr_e[ii][1] % 4 == 0);

@@ -866,7 +866,7 @@ edf_swin3d_grad_kernel(const __grid_constant__ EdfParams p, const __grid_constan
     }
 }
 
-static bool g_swin_configured = false;
+static EdfPerDeviceFlag g_swin_configured;
 
 // shared conditions of the two staged-window kernels
 static bool edf_swin_common_ok(const EdfParams& p, const EdfFastLaunch& L, int ii)
@@ -986,7 +986,7 @@ static int edf_swin_launch(int order, int gradient, cudaStream_t st, const EdfPa
         if (dbg) L.input_mask |= 0x80000000u;           // the "does not fit the window" path
     }
     const size_t smem = sizeof(EdfSwinSmem);
-    if (!g_swin_configured) {
+    if (!g_swin_configured.test()) {
 #define EDF_SW_ATTR(O)                                                                                              \
     cudaFuncSetAttribute(edf_swin3d_fwd_kernel<O, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
     cudaFuncSetAttribute(edf_swin3d_fwd_kernel<O, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
@@ -998,7 +998,7 @@ static int edf_swin_launch(int order, int gradient, cudaStream_t st, const EdfPa
         EDF_SW_ATTR(0); EDF_SW_ATTR(1); EDF_SW_ATTR(2); EDF_SW_ATTR(3); EDF_SW_ATTR(4); EDF_SW_ATTR(5);
 #undef EDF_SW_ATTR
         if (cudaGetLastError() != cudaSuccess) return -1;
-        g_swin_configured = true;
+        g_swin_configured.set();
     }
     const bool cm = p.inp[ii].mode == EDF_MODE_CONSTANT;
 #define EDF_SW_CASE(K, O)                                                                \
