@@ -76,17 +76,18 @@ def plane_hull(coef0, level=None):
     the axis-0 displacement component.  Returns (lo[n0], hi[n0], level)."""
     c = numpy.asarray(coef0, dtype=numpy.float64)
     r = choose_level(c.shape, 4 if max(c.shape) <= 3 else 3) if level is None else int(level)
-    if c.ndim == 3:
-        # the common case as three plain matrix products (half the time of the generic contraction)
-        M0, M1, M2 = (refine_matrix(P, r) for P in c.shape)
-        F = (M0 @ c.reshape(c.shape[0], -1)).reshape(M0.shape[0], c.shape[1], c.shape[2])
-        F = numpy.matmul(M1, F @ M2.T)
-    else:
-        F = c
-        for a in range(c.ndim):
-            F = numpy.moveaxis(numpy.tensordot(refine_matrix(c.shape[a], r), F, axes=([1], [a])), 0, a)
-    F = F.reshape(F.shape[0], -1)
-    return F.min(axis=1), F.max(axis=1), r
+    with numpy.errstate(invalid='ignore', over='ignore'):      # non-finite coefficients: the caller checks the result
+        if c.ndim == 3:
+            # the common case as three plain matrix products (half the time of the generic contraction)
+            M0, M1, M2 = (refine_matrix(P, r) for P in c.shape)
+            F = (M0 @ c.reshape(c.shape[0], -1)).reshape(M0.shape[0], c.shape[1], c.shape[2])
+            F = numpy.matmul(M1, F @ M2.T)
+        else:
+            F = c
+            for a in range(c.ndim):
+                F = numpy.moveaxis(numpy.tensordot(refine_matrix(c.shape[a], r), F, axes=([1], [a])), 0, a)
+        F = F.reshape(F.shape[0], -1)
+        return F.min(axis=1), F.max(axis=1), r
 
 
 def slab_bounds(coef0, dim0, offset0, slabs, level=None):
@@ -118,4 +119,36 @@ def slab_bounds(coef0, dim0, offset0, slabs, level=None):
         if ja >= jb:                                  # cannot happen for positions inside [0, P_0 - 1]
             ja, jb = 0, n0
         out.append((min(lo[ja:jb]), max(hi[ja:jb])))
+    return out
+
+
+def integer_reach(bounds, order):
+    """(lo, hi) per slab: every input plane a voxel of the slab reads or scatters to, taps included, lies in
+    [o + offset0 + lo, o + offset0 + hi] (o = the voxel's output plane).  The window of an order-n spline
+    starts at floor(c) - n/2 or floor(c + 0.5) - n/2 and spans n + 1 taps (deform.c:784-788): n + 2 planes on
+    either side of the displaced coordinate cover it with room to spare."""
+    pad = int(order) + 2
+    return [(int(numpy.floor(lo)) - pad, int(numpy.ceil(hi)) + pad) for lo, hi in bounds]
+
+
+def forward_waits(slabs, reach, in0, offset0, h):
+    """Forward pipeline: index of the last UPLOAD slab (height h, in0 input planes) that output slab k has to
+    wait for -- the slab holding the highest input plane it can read."""
+    return [min(in0 - 1, max(0, b - 1 + offset0 + hi)) // h for (a, b), (_, hi) in zip(slabs, reach)]
+
+
+def gradient_final_slabs(slabs, reach, in0, offset0, h):
+    """Gradient pipeline: after output slab k has been scattered, how many leading dX slabs (height h) are
+    final, i.e. below the lowest input plane any LATER output slab can still add to.  Non-decreasing in k;
+    all of them after the last slab."""
+    n_out = len(slabs)
+    n_in = -(-in0 // h)
+    lowest = [in0] * (n_out + 1)
+    for k in range(n_out - 1, -1, -1):
+        lowest[k] = min(lowest[k + 1], slabs[k][0] + offset0 + reach[k][0])
+    out, done = [], 0
+    for k in range(n_out):
+        j = n_in if k == n_out - 1 else min(n_in, max(0, lowest[k + 1]) // h)
+        done = max(done, j)
+        out.append(done)
     return out

@@ -344,8 +344,7 @@ def _slab_reach(displacement_f, order, dim0, off0, slabs):
         _BOUNDS_CACHE[key] = b
         while len(_BOUNDS_CACHE) > 8:
             _BOUNDS_CACHE.popitem(last=False)
-    pad = int(max(order)) + 2
-    return [(int(numpy.floor(lo)) - pad, int(numpy.ceil(hi)) + pad) for lo, hi in b]
+    return _reach.integer_reach(b, max(order))
 
 
 class _SlabLauncher(object):
@@ -417,17 +416,16 @@ def _pipelined_forward(lib, device, Xs, displacement, output_shapes, output_offs
         _mark("prefilter along axis 0 done", cur)
         filtered = 0
     job = _SlabLauncher(lib, 0, F_d, Y_d, displacement_f, output_offset, axis, order, mode, cval, flags)
-    for (a, b), (_, hi) in zip(slabs, reach):
-        need = min(in0 - 1, max(0, b - 1 + off0 + hi))      # last input plane the slab can read
-        cur.wait_event(up_done[need // h])
-        while filtered <= need // h:                        # ... the other passes slab by slab, in place
+    for (a, b), w in zip(slabs, _reach.forward_waits(slabs, reach, in0, off0, h)):
+        cur.wait_event(up_done[w])                          # the upload slab with the last input plane [a, b) can read
+        while filtered <= w:                                # ... the other passes slab by slab, in place
             fa, fb = filtered * h, min(in0, (filtered + 1) * h)
             for i, (fd, o) in enumerate(zip(F_d, pf)):
                 for d in axis[i][1:]:
                     if o:
                         _spline_filter1d_device(lib, fd[fa:fb], fd[fa:fb], d, o)
             filtered += 1
-        _mark("kernel [%d,%d) after upload %d: start" % (a, b, need // h), cur)
+        _mark("kernel [%d,%d) after upload %d: start" % (a, b, w), cur)
         job.launch(a, b)
         _mark("kernel [%d,%d) done" % (a, b), cur)
         ev = torch.cuda.Event()
@@ -476,10 +474,7 @@ def _pipelined_gradient(lib, device, dYs, X_shape, displacement, output_offset, 
     dX_hn = [_pinned_result(sh, g.dtype) for sh, g in zip(X_shape, G_h)]
     dX_h = [p[0] for p in dX_hn]
     n_in = -(-in0 // h)
-    # lowest input plane that output slabs k+1 .. can still scatter to: everything below is final after slab k
-    lowest = [in0] * (n_out + 1)
-    for k in range(n_out - 1, -1, -1):
-        lowest[k] = min(lowest[k + 1], slabs[k][0] + off0 + reach[k][0])
+    final = _reach.gradient_final_slabs(slabs, reach, in0, off0, h)   # dX slabs no later output slab can touch
     flushed = 0                                             # dX slabs [0, flushed) are already on their way home
     job = _SlabLauncher(lib, 1, dX_d, G_d, displacement_f, output_offset, axis, order, mode, cval, flags)
     for k, (a, b) in enumerate(slabs):
@@ -487,7 +482,7 @@ def _pipelined_gradient(lib, device, dYs, X_shape, displacement, output_offset, 
         _mark("kernel [%d,%d): start" % (a, b), cur)
         job.launch(a, b)
         _mark("kernel [%d,%d) done" % (a, b), cur)
-        j_end = n_in if k == n_out - 1 else min(n_in, max(0, lowest[k + 1]) // h)
+        j_end = final[k]
         if any(pf):
             # adjoint of the prefilter (ref:277-286): its pass along axis 0 needs the complete dX, the other
             # passes and the download then go slab by slab

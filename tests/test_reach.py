@@ -76,3 +76,35 @@ def test_non_finite_coefficients_are_refused():
     assert _reach.slab_bounds(c, 64, 0, [(0, 32), (32, 64)]) is None
     c[1, 1, 1] = np.nan
     assert _reach.slab_bounds(c, 64, 0, [(0, 32), (32, 64)]) is None
+
+
+@pytest.mark.parametrize("sigma,order,off,out0,h", [(8.0, 3, 0, 64, 8), (25.0, 3, 0, 64, 8), (8.0, 0, 10, 40, 7),
+                                                   (30.0, 1, 5, 50, 8), (3.0, 5, 0, 64, 16)])
+def test_pipeline_schedules_respect_the_true_field(sigma, order, off, out0, h):
+    """forward_waits / gradient_final_slabs against the voxel-by-voxel field: an output slab never reads an
+    input plane that has not been uploaded when it starts, and a dX slab is never sent home while a later
+    output slab can still add to it (plane ranges include the spline's taps; coordinates outside the volume
+    are clamped to it, as 'nearest' does -- 'constant' touches nothing there)."""
+    P, N = (5, 4, 5), (64, 24, 20)
+    c, d = _field(P, N, sigma, 11)
+    in0 = N[0]
+    slabs = [(a, min(out0, a + h)) for a in range(0, out0, h)]
+    bounds = _reach.slab_bounds(c, in0, off, slabs)
+    reach = _reach.integer_reach(bounds, order)
+    o = np.arange(out0)[:, None, None] + off
+    src = o + d[off:off + out0]
+    first = np.floor(src).astype(int) - order // 2 - 1              # generous: one plane beyond the window start
+    last = first + order + 2
+    first, last = np.clip(first, 0, in0 - 1), np.clip(last, 0, in0 - 1)
+    waits = _reach.forward_waits(slabs, reach, in0, off, h)
+    final = _reach.gradient_final_slabs(slabs, reach, in0, off, h)
+    n_in = -(-in0 // h)
+    assert final[-1] == n_in and all(final[k] <= final[k + 1] for k in range(len(final) - 1))
+    for k, (a, b) in enumerate(slabs):
+        assert 0 <= waits[k] < n_in
+        assert last[a:b].max() < (waits[k] + 1) * h, (k, "forward slab starts before its inputs arrived")
+        if k + 1 < len(slabs):
+            assert first[b:].min() >= final[k] * h, (k, "dX slab downloaded before its last contribution")
+    # and the schedules are not vacuous: for the gentle field something overlaps
+    if sigma <= 8.0 and out0 == 64 and h == 8:
+        assert waits[0] < n_in - 1 and final[len(slabs) // 2] > 0
