@@ -15,23 +15,27 @@ from .deform_grid import deform_grid_gradient as _deform_grid_gradient
 
 
 class ElasticDeform(torch.autograd.Function):
+    """``ElasticDeform.apply(displacement, args, kwargs, *xs)`` -> tuple of deformed tensors (ref:5-30).
+
+    The inputs stay where they are: CUDA tensors are handed to the C-ABI as device pointers on the
+    current stream, and the outputs / input gradients are CUDA tensors.  Only the gradient with respect
+    to the inputs exists (``None`` for the displacement and the two argument containers)."""
+
     @staticmethod
     def forward(ctx, displacement, deform_args, deform_kwargs, *xs):
         ctx.save_for_backward(displacement)
-        ctx.deform_args = deform_args
-        ctx.deform_kwargs = deform_kwargs
-        ctx.x_shapes = [tuple(x.shape) for x in xs]
-
-        ys = _deform_grid([x.detach() for x in xs], displacement.detach(),
-                             *deform_args, **deform_kwargs)
-        return tuple(ys)
+        ctx.call = (tuple(deform_args), dict(deform_kwargs))
+        ctx.input_shapes = [tuple(x.shape) for x in xs]
+        outputs = _deform_grid([x.detach() for x in xs], displacement.detach(), *ctx.call[0], **ctx.call[1])
+        return tuple(outputs)
 
     @staticmethod
     def backward(ctx, *dys):
-        displacement, = ctx.saved_tensors
-        dxs = _deform_grid_gradient([dy.detach() for dy in dys], displacement.detach(),
-                                       *ctx.deform_args, X_shape=ctx.x_shapes, **ctx.deform_kwargs)
-        return (None, None, None) + tuple(dxs)
+        (displacement,) = ctx.saved_tensors
+        args, kwargs = ctx.call
+        grads = _deform_grid_gradient([dy.detach() for dy in dys], displacement.detach(), *args,
+                                      X_shape=ctx.input_shapes, **kwargs)
+        return (None, None, None) + tuple(grads)
 
 
 def deform_grid(X, displacement, *args, **kwargs):
@@ -51,14 +55,7 @@ def deform_grid(X, displacement, *args, **kwargs):
 
     See ``elasticdeform_b200.deform_grid`` for the other parameters.
     """
-    if not isinstance(X, (list, tuple)):
-        X_list = [X]
-    else:
-        X_list = X
-    displacement = torch.as_tensor(displacement)
-    y = ElasticDeform.apply(displacement, args, kwargs, *X_list)
-
-    if isinstance(X, (list, tuple)):
-        return y
-    else:
-        return y[0]
+    single = not isinstance(X, (list, tuple))
+    inputs = [X] if single else list(X)
+    outputs = ElasticDeform.apply(torch.as_tensor(displacement), args, kwargs, *inputs)
+    return outputs[0] if single else outputs

@@ -157,3 +157,36 @@ def test_dtype_codes():
         _lib.dtype_code(np.float16)
     with pytest.raises(RuntimeError, match="data type not supported"):
         _lib.dtype_code(np.complex64)
+
+
+def test_torch_wrapper_plumbing_without_gpu(monkeypatch):
+    """elasticdeform_b200.torch: container conventions and the autograd contract of the reference wrapper
+    (torch.py:33-66, :5-30), with the two compute entry points replaced by stand-ins (no GPU here)."""
+    import torch
+    import elasticdeform_b200.torch as etorch
+    seen = {}
+
+    def fake_forward(xs, displacement, *args, **kwargs):
+        seen["fwd"] = (len(xs), tuple(displacement.shape), args, dict(kwargs))
+        assert all(not x.requires_grad for x in xs) and not displacement.requires_grad
+        return [x * 2.0 for x in xs]
+
+    def fake_gradient(dys, displacement, *args, X_shape=None, **kwargs):
+        seen["grad"] = (len(dys), X_shape, args, dict(kwargs))
+        return [dy * 2.0 for dy in dys]
+
+    monkeypatch.setattr(etorch, "_deform_grid", fake_forward)
+    monkeypatch.setattr(etorch, "_deform_grid_gradient", fake_gradient)
+    D = np.zeros((2, 3, 3))
+    a = torch.ones(4, 5, requires_grad=True)
+    b = torch.ones(4, 5, dtype=torch.float64, requires_grad=True)
+    out = etorch.deform_grid(a, D, 1, mode="nearest")                      # single in -> single out
+    assert isinstance(out, torch.Tensor) and out.shape == (4, 5)
+    assert seen["fwd"] == (1, (2, 3, 3), (1,), {"mode": "nearest"})
+    outs = etorch.deform_grid((a, b), torch.as_tensor(D), order=[1, 3])    # tuple in -> tuple out
+    assert isinstance(outs, tuple) and len(outs) == 2 and outs[1].dtype == torch.float64
+    (outs[0].sum() + 3.0 * outs[1].sum()).backward()
+    assert seen["grad"][0] == 2 and seen["grad"][1] == [(4, 5), (4, 5)] and seen["grad"][3] == {"order": [1, 3]}
+    assert torch.equal(a.grad, torch.full((4, 5), 2.0)) and torch.equal(b.grad, torch.full((4, 5), 6.0, dtype=torch.float64))
+    res = etorch.ElasticDeform.apply(torch.as_tensor(D), (), {}, a)        # the Function itself: always a tuple
+    assert isinstance(res, tuple) and len(res) == 1
