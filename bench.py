@@ -383,8 +383,8 @@ def run_gpu_arm(args):
             pass
         ach_f = ALG_BYTES_FWD / (t_fwd * 1e-3) / 1e9
         ach_g = ALG_BYTES_GRAD / (t_grad * 1e-3) / 1e9
-        cpu = None
-        if world == 1 or True:
+        cpu = None                                               # timed at N=1 only (rank 0); null in the N>1 lines
+        if world == 1:
             try:
                 v, cores, kind, sample, t, _ = best_cpu_reference_rate(X_h, dY_h, D, seconds_budget=30.0, steps=1)
                 cpu = {"value": round(v, 4), "unit": "Mvoxels/s", "cores": cores, "kind": kind, "sample": sample}
