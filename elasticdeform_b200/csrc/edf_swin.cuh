@@ -41,6 +41,9 @@
 #ifndef EDF_SW_ROWS
 #define EDF_SW_ROWS 364            // window capacity in rows; 2 CTAs x 112 KB per SM
 #endif
+#ifndef EDF_SW_MINBLOCKS
+#define EDF_SW_MINBLOCKS 2         // resident CTAs per SM the register allocation aims at (3 needs EDF_SW_ROWS <= 208
+#endif                             //   and 85 registers per thread: see DESIGN.md (f) for what that costs in spills)
 #define EDF_SW_MAXQ (EDF_SW_PITCH / 4)
 #ifndef EDF_SWIN_GRAD_MAXORDER
 #define EDF_SWIN_GRAD_MAXORDER 3      // highest spline order the staged-window gradient kernel takes over by default
@@ -331,7 +334,7 @@ __device__ __forceinline__ void edf_swin_tile(const EdfTileSched& T, int& x0, in
 // CMODE: boundary mode 'constant' (out-of-range voxels take cval: no coordinate map, and no call inside
 // the coordinate phase, which keeps its register allocation free of call-crossing live ranges)
 template <int ORDER, bool CMODE>
-__global__ void __launch_bounds__(EDF_SW_THREADS, 2)
+__global__ void __launch_bounds__(EDF_SW_THREADS, EDF_SW_MINBLOCKS)
 edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -614,7 +617,7 @@ edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
 // cells whose row / column is folded back by the reference's mirror map (deform.c:796-810) at flush time.
 // =======================================================================================
 template <int ORDER, bool CMODE>
-__global__ void __launch_bounds__(EDF_SW_THREADS, 2)
+__global__ void __launch_bounds__(EDF_SW_THREADS, EDF_SW_MINBLOCKS)
 edf_swin3d_grad_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
