@@ -19,6 +19,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
+    "--split-compile", "0",          # ptxas of the (many) kernel instantiations in parallel: 4 min -> 1 min
 ]
 
 

@@ -15,6 +15,8 @@
 #include "edf_fast.cuh"
 #include "edf_lean.cuh"
 #include "edf_swin.cuh"
+#include "edf_poly.cuh"
+#include "edf_tile.cuh"
 
 // ----------------------------------------------------------------------------
 // error plumbing

@@ -594,6 +594,12 @@ static bool edf_swin_fwd_env();
 static int edf_swin_max_fwd_order();
 static bool edf_swin_grad_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii, bool all_orders);
 static int edf_swin_launch(int order, int gradient, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii);
+// polynomial-coordinate kernels (edf_poly.cuh)
+static bool edf_poly_direct_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii);
+static int edf_poly_direct_launch(int order, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii);
+// staged-window kernels of round 2 (edf_tile.cuh): tensor-map TMA staging, polynomial coordinates
+static bool edf_tile_fwd_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii);
+static int edf_tile_launch_fwd(int order, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii);
 
 // Tries to run (part of) the problem on the specialised kernels.
 //   *handled_mask receives the inputs that were processed (the caller runs the generic
@@ -642,20 +648,33 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
             int rcs = -2;
             const bool steep = (flags & EDF_FLAG_STEEP) != 0;
             const int ord = p.inp[ii].order;
-            if (windows && !p.gradient) {
+            bool poly = false, tile = false;
+            if (!p.gradient && ord <= 1 && !(flags & EDF_FLAG_STAGED_FWD) && edf_poly_direct_eligible(p, L, ii)) {
+                // orders 0 / 1, 'constant' mode: polynomial coordinates, direct gather
+                rcs = edf_poly_direct_launch(ord, st, p, L, ii);
+                poly = rcs == 0;
+            } else if (windows && !p.gradient) {
                 // (and unless the volume is small: below ~two waves of CTAs the per-CTA prologue and the two barriers
                 //  per chunk weigh more than the cheaper taps -- 128^3, order 3: 0.169 ms staged against 0.137 ms direct)
                 const bool big = (uint64_t)p.odim[0] * (uint64_t)p.odim[1] * (uint64_t)p.odim[2] >= EDF_SWIN_FWD_MIN_VOXELS;
                 const bool want = (flags & EDF_FLAG_STAGED_FWD) || edf_swin_fwd_env() ||
                                   (!steep && big && ord >= 2 && ord <= edf_swin_max_fwd_order());
-                if (want && edf_swin_eligible(p, L, ii)) rcs = edf_swin_launch(ord, 0, st, p, L, ii);
+                if (want && edf_tile_fwd_eligible(p, L, ii)) {
+                    rcs = edf_tile_launch_fwd(ord, st, p, L, ii);
+                    tile = rcs == 0;
+                }
+                if (rcs == -2 && want && edf_swin_eligible(p, L, ii)) rcs = edf_swin_launch(ord, 0, st, p, L, ii);
             } else if (windows && p.gradient && !(flags & EDF_FLAG_FIXED_WINDOW) &&
                        ((flags & EDF_FLAG_STAGED_ALL) || !(steep && ord >= 2))) {
                 if (edf_swin_grad_eligible(p, L, ii, (flags & EDF_FLAG_STAGED_ALL) != 0))
                     rcs = edf_swin_launch(ord, 1, st, p, L, ii);
             }
             if (rcs == -1) return -1;
-            if (rcs == 0) {
+            if (rcs == 0 && poly) {
+                *name = "poly3d_f32_direct";
+            } else if (rcs == 0 && tile) {
+                *name = p.gradient ? "tile3d_f32_grad" : "tile3d_f32";
+            } else if (rcs == 0) {
                 *name = p.gradient ? "swin3d_f32_grad" : "swin3d_f32";
             } else if (windows && p.gradient && edf_gradwin_eligible(p)) {
                 const int rcw = edf_lean_launch_gradwin(p.inp[ii].order, st, p, L, ii);
