@@ -72,7 +72,7 @@ class EdfProblem(ctypes.Structure):
 EXPORTED_SYMBOLS = (
     "edf_deform_grid", "edf_deform_grid_grad", "edf_deform_grid_batch",
     "edf_spline_filter1d", "edf_spline_filter1d_grad", "edf_last_error",
-    "edf_version", "edf_device_ok", "edf_launch_count", "edf_last_kernel",
+    "edf_version", "edf_device_ok", "edf_launch_count", "edf_last_kernel", "edf_debug_tile_profile",
 )
 
 _lib = None

@@ -29,6 +29,18 @@ extern "C" const char* edf_last_kernel(void) { return g_last_kernel; }
 extern "C" uint64_t edf_launch_count(void) { return g_launches.load(); }
 extern "C" int edf_version(void) { return 100; /* 0.1.0 */ }
 
+// debug: phase-cycle totals of the staged-window kernels of builds with -DEDF_TILE_PROFILE (zeros otherwise);
+// reads and resets.  out[0..7] = cycles per phase summed over warps, out[15] = warps.
+extern "C" int edf_debug_tile_profile(uint64_t* out16)
+{
+    unsigned long long h[16];
+    if (cudaMemcpyFromSymbol(h, g_tile_prof, sizeof(h)) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (int i = 0; i < 16; ++i) out16[i] = h[i];
+    memset(h, 0, sizeof(h));
+    if (cudaMemcpyToSymbol(g_tile_prof, h, sizeof(h)) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return 0;
+}
+
 extern "C" int edf_device_ok(void)
 {
     int dev = 0;

@@ -24,12 +24,13 @@
 #define EDF_PL_THREADS (EDF_PL_TX * EDF_PL_G)
 #define EDF_PL_RY 64               // rows a CTA walks through (table capacity)
 #define EDF_PL_NC 8                // control columns the 32 lanes of a warp can touch (span + 4)
+#define EDF_PL_MAXWARPS 16         // warps per CTA of the largest kernel using these tables
 
 struct EdfPolyTables {
     double u[EDF_PL_RY];           // fractional control position of each row of the tile
     double wz[EDF_PL_G][4];        // z weights of each slab (deform.c:160-268, order 3)
     double wx[EDF_PL_TX][4];       // x weights of each lane
-    double T[EDF_PL_G][3][4][EDF_PL_NC];   // warp-private: z-contracted control coefficients of the current y interval
+    double T[EDF_PL_MAXWARPS][3][4][EDF_PL_NC];   // warp-private: z-contracted control coefficients of the current y interval
     int    jy[EDF_PL_RY];          // first control row of each row's window (floor(cp) - 1)
     int    sz[EDF_PL_G];
     int    sx[EDF_PL_TX];
@@ -59,9 +60,10 @@ __device__ __forceinline__ void edf_poly_tables(const EdfParams& p, EdfPolyTable
 // Rebuild the polynomial coefficients of this thread's column for the control interval whose window starts at
 // control row j0.  Warp-collective (all 32 lanes).  Returns the warp's gate: false when every control
 // coefficient the warp touches is zero (then a == 0 exactly).
-__device__ __forceinline__ bool edf_poly_build(const EdfParams& p, EdfPolyTables& s, int g, int lane, int j0, double* a /*[3][4]*/)
+__device__ __forceinline__ bool edf_poly_build(const EdfParams& p, EdfPolyTables& s, int g, int lane, int j0, double* a /*[3][4]*/, int tw = -1)
 {
     static_assert(EDF_PL_NC == 8, "lane -> (control row, control column) mapping");
+    if (tw < 0) tw = g;                                            // table slot of this warp
     const int j = lane >> 3, kx = lane & 7;
     const int sx0 = s.sx[0];
     const int nxw = s.sx[EDF_PL_TX - 1] - sx0 + 4;
@@ -89,7 +91,7 @@ __device__ __forceinline__ bool edf_poly_build(const EdfParams& p, EdfPolyTables
                 nz |= (cf != 0.0);
                 acc = fma(cf, w[i], acc);
             }
-            s.T[g][h][j][kx] = acc;
+            s.T[tw][h][j][kx] = acc;
         }
     }
     const bool gate = __any_sync(0xffffffffu, nz);
@@ -105,7 +107,7 @@ __device__ __forceinline__ bool edf_poly_build(const EdfParams& p, EdfPolyTables
         for (int jj = 0; jj < 4; ++jj) {
             double e = 0.0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) e = fma(s.T[g][h][jj][sxrel + k], wx[k], e);
+            for (int k = 0; k < 4; ++k) e = fma(s.T[tw][h][jj][sxrel + k], wx[k], e);
             E[jj] = e;
         }
         // uniform cubic B-spline segment -> power basis in u (weights as in deform.c:171-177)

@@ -12,25 +12,42 @@
 //     short patch pass that only border chunks run; planes outside the volume are fetched from their mirror
 //     plane directly.  (The innermost box coordinate must be a multiple of 4 floats: an unaligned one traps
 //     with cudaErrorIllegalInstruction -- scripts/experiments/tma_tensor_test.cu, profiles/r2/.)
-//   * chunks of 8 slabs x 8 rows x 32 columns (2048 voxels, 8 per thread): 44 staged bytes per voxel instead
-//     of 70 for 4-row chunks with the same boxes; a chunk whose box outgrows the window is processed as two
-//     4-row halves (their boxes are reduced alongside the full one), then falls back to the direct gather.
-// Two CTAs per SM: one CTA's coordinate phase and TMA wait overlap the other's gather.
+//   * cubic weights in 11 operations per axis (power form) instead of 17.
+// Chunks of 8 slabs x 4 rows x 32 columns as in edf_swin.cuh (8-row chunks halve the staged bytes per voxel, but
+// their boxes outgrow a 100 KB window in a third of the chunks of the headline field; measured slower).  A chunk
+// whose box outgrows the window is processed as two 2-row halves, then falls back to the direct gather.
+// Two CTAs per SM: one CTA's coordinate phase and TMA wait overlap the other's gather.  (A warp-specialised
+// producer / consumer pipeline over the same pieces is kept under csrc/experimental/: correct, but latency bound
+// at the two stages that fit in shared memory -- see DESIGN.md.)
 #pragma once
 #include <cuda.h>
 #include "edf_poly.cuh"
 
-#define EDF_TL_MR 8                // rows per chunk (voxels per thread and chunk)
+#define EDF_TL_MR 4                // rows per chunk (voxels per thread and chunk)
 #define EDF_TL_PITCH 64            // floats between window rows
 #define EDF_TL_BY 4                // rows per TMA box
 #ifndef EDF_TL_ROWS
-#define EDF_TL_ROWS 400            // window capacity in rows (100 KB); 2 CTAs per SM
+#define EDF_TL_ROWS 380            // window capacity in rows (95 KB); 2 CTAs per SM
 #endif
 #define EDF_TL_MAXQ (EDF_TL_PITCH / 4)
 
+// Phase timing (debug builds with -DEDF_TILE_PROFILE): lane 0 of every warp accumulates the cycles it spends in
+// each phase; edf_debug_tile_profile() reads and resets the totals.
+__device__ unsigned long long g_tile_prof[16];
+#ifdef EDF_TILE_PROFILE
+#define EDF_TP_DECL long long tp_t = clock64(); long long tp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define EDF_TP_MARK(k) { const long long t_ = clock64(); tp_acc[k] += t_ - tp_t; tp_t = t_; }
+#define EDF_TP_FLUSH if ((threadIdx.x & 31) == 0) { for (int k_ = 0; k_ < 8; ++k_) atomicAdd(&g_tile_prof[k_], (unsigned long long)tp_acc[k_]); atomicAdd(&g_tile_prof[15], 1ull); }
+#else
+#define EDF_TP_DECL
+#define EDF_TP_MARK(k)
+#define EDF_TP_FLUSH
+#endif
+
 struct EdfTileSmem {
     EdfPolyTables t;
-    int bb[3][2][8];               // [chunk % 3][half: rows 0-3 / 4-7]: min z,y,x start, max z,y,x start, (gradient: max |dY| bits)
+    int bb[3][8];                  // [chunk % 3]: min z,y,x start, max z,y,x start, (gradient: max |dY| bits) of the chunk's active voxels
+    int hb[2][8];                  // the same per 2-row half, only when the full box does not fit the window
     unsigned long long mbar;
 };
 
@@ -186,7 +203,36 @@ __device__ __forceinline__ void edf_tile_patch(float* win, const EdfTileBox& b, 
                 win[r * EDF_TL_PITCH + c] = win[(zr * b.nyal + ym) * EDF_TL_PITCH + cm];
         }
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes before the next TMA fill of these cells
     __syncthreads();
+}
+
+// cubic B-spline weights from the fractional offset, 11 operations per axis (the reference's closed forms,
+// deform.c:171-177, expanded in powers of t; differences to the reference's float evaluation are ~1 ulp)
+__device__ __forceinline__ void edf_tile_weights3(float t, float* w)
+{
+    const float t2 = t * t, t3 = t2 * t;
+    w[3] = t3 * (1.0f / 6.0f);
+    w[0] = fmaf(-t3, 1.0f / 6.0f, fmaf(t2, 0.5f, fmaf(t, -0.5f, 1.0f / 6.0f)));
+    w[1] = fmaf(t3, 0.5f, fmaf(t2, -1.0f, 2.0f / 3.0f));
+    w[2] = fmaf(t3, -0.5f, fmaf(t2, 0.5f, fmaf(t, 0.5f, 1.0f / 6.0f)));
+}
+template <int ORDER>
+__device__ __forceinline__ void edf_tile_weights(float t, float* w)
+{
+    if (ORDER == 3) edf_tile_weights3(t, w);
+    else edf_bspline_weights_f32<ORDER>(t, w);
+}
+
+// voxel whose chunk does not fit the window at all (very steep field): taps straight from global memory.  Out of
+// line with scalar arguments, so that the per-voxel state arrays of the caller keep static indices (registers).
+template <int ORDER>
+__device__ __noinline__ float edf_tile_direct_voxel(const float* __restrict__ pin, unsigned pk, float fz, float fy, float fx,
+                                                    int z, int y, int x, int lenz, int leny, int lenx, int isz, int isy)
+{
+    const int stz = z - EDF_SW_PK_BIAS + (int)(pk >> 20), sty = y - EDF_SW_PK_BIAS + (int)((pk >> 10) & 1023u);
+    const int stx = x - EDF_SW_PK_BIAS + (int)(pk & 1023u);
+    return edf_swin_direct_gather<ORDER>(pin, stz, sty, stx, fz, fy, fx, lenz, leny, lenx, isz, isy);
 }
 
 template <int ORDER, bool CMODE>
@@ -204,14 +250,16 @@ edf_tile3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
     const int ry = (int)L.rows_per_cta;
 
     if (tid == 0) edf_mbar_init(&s.mbar, EDF_PL_G);
-    if (tid < 3 * 2 * 8) (&s.bb[0][0][0])[tid] = ((tid & 7) < 3) ? INT_MAX : INT_MIN;
+    if (tid < 3 * 8) (&s.bb[0][0])[tid] = ((tid & 7) < 3) ? INT_MAX : INT_MIN;
+    if (tid >= 32 && tid < 48) (&s.hb[0][0])[tid - 32] = ((tid & 7) < 3) ? INT_MAX : INT_MIN;
+    EDF_TP_DECL
     edf_poly_tables(p, s.t, z0, y0, x0, ry);                      // ends with a CTA barrier
+    EDF_TP_MARK(0)
 
     const int x = x0 + lane, z = z0 + g;
     const int odz = (int)p.odim[0], ody = (int)p.odim[1], odx = (int)p.odim[2];
     const bool tok = (x < odx) && (z < odz);
     const int nrow = min(ry, ody - y0);
-    const int nchunk = (nrow + EDF_TL_MR - 1) / EDF_TL_MR;
 
     const EdfInputDesc& d = p.inp[ii];
     const float* __restrict__ pin = (const float*)d.in;
@@ -225,7 +273,6 @@ edf_tile3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
     const float cvalf = __uint_as_float((uint32_t)L.cval_bits[ii]);
     const double bz = xadd((double)z, p.ooff_d[0]);
     const double bx = xadd((double)x, p.ooff_d[2]);
-    const double offy = p.ooff_d[1];
     const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(win);
     const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(&s.mbar);
 
@@ -234,37 +281,41 @@ edf_tile3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
     bool gate = false;
     int par = 0;
     unsigned mphase = 0;
+    int nb = EDF_TL_MR;
+    double by = xadd((double)y0, p.ooff_d[1]);                     // exact: integers
 
-    for (int c = 0; c < nchunk; ++c) {
-        const int yc0 = y0 + c * EDF_TL_MR;
-        // ---- phase A: coordinates and classification of this thread's 8 voxels
+    for (int m0 = 0; m0 < nrow; m0 += nb) {
+        const int yc0 = y0 + m0;
+        // rows of this chunk: up to 4, all inside one control interval of the y axis (CTA-uniform), so that one
+        // polynomial serves the chunk; the rebuild below is its only call site
+        {
+            const int jr = s.t.jy[m0];
+            if (jr != jcur) {
+                gate = edf_poly_build(p, s.t, g, lane, jr, a);
+                jcur = jr;
+            }
+            nb = min(EDF_TL_MR, nrow - m0);
+#pragma unroll
+            for (int u = EDF_TL_MR - 1; u >= 1; --u)
+                if (u < nb && s.t.jy[m0 + u] != jr) nb = u;
+        }
+        // ---- phase A: coordinates and classification of this thread's voxels
         unsigned pk[EDF_TL_MR];
         float fz[EDF_TL_MR], fy[EDF_TL_MR], fx[EDF_TL_MR];
         unsigned actm = 0, cstm = 0, slowm = 0;
-        int mn[2][3], mx[2][3];
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int q = 0; q < 3; ++q) { mn[h][q] = INT_MAX; mx[h][q] = INT_MIN; }
+        int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+        double yd = by;
 #pragma unroll
         for (int u = 0; u < EDF_TL_MR; ++u) {
-            const int m = min(c * EDF_TL_MR + u, nrow - 1);
+            const int m = m0 + min(u, nb - 1);
             const int y = y0 + m;
-            const bool valid = tok && (c * EDF_TL_MR + u < nrow);
-            const int jr = s.t.jy[m];
-            if (jr != jcur) {                                      // warp-uniform: the row entered another control interval
-                double tmp[12];
-                gate = edf_poly_build_nl(p, s.t, g, lane, jr, tmp);
-#pragma unroll
-                for (int q = 0; q < 12; ++q) a[q] = tmp[q];
-                jcur = jr;
-            }
+            const bool valid = tok && (u < nb);
             double dz, dy, dx;
             edf_poly_eval(a, s.t.u[m], dz, dy, dx);
             double inz, iny, inx;
             if (!affine) {
                 inz = xadd(bz, dz);
-                iny = xadd(xadd((double)y, offy), dy);
+                iny = xadd(yd, dy);
                 inx = xadd(bx, dx);
             } else {
                 const int o[3] = {z, y, x};
@@ -272,6 +323,7 @@ edf_tile3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
                 iny = edf_source_coordinate<3, int>(p, o, 1, dy);
                 inx = edf_source_coordinate<3, int>(p, o, 2, dx);
             }
+            if (u + 1 < nb) yd = xadd(yd, 1.0);
             int stz, sty, stx;
             bool slow, cst, oob;
             edf_tile_classify<ORDER, CMODE>(d.mode, inz, iny, inx, limz, limy, limx, lenz, leny, lenx, gate,
@@ -282,41 +334,64 @@ edf_tile3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
             if (valid & !slow & cst) cstm |= 1u << u;
             if (valid & !slow & !cst) {
                 actm |= 1u << u;
-                const int h = u >> 2;
-                mn[h][0] = min(mn[h][0], stz); mn[h][1] = min(mn[h][1], sty); mn[h][2] = min(mn[h][2], stx);
-                mx[h][0] = max(mx[h][0], stz); mx[h][1] = max(mx[h][1], sty); mx[h][2] = max(mx[h][2], stx);
+                mn[0] = min(mn[0], stz); mn[1] = min(mn[1], sty); mn[2] = min(mn[2], stx);
+                mx[0] = max(mx[0], stz); mx[1] = max(mx[1], sty); mx[2] = max(mx[2], stx);
             }
         }
-        // ---- phase B: exact bounding boxes (rows 0-3, rows 4-7) of the chunk's tap windows
+        by = xadd(by, (double)nb);
+        // ---- phase B: exact bounding box of the chunk's tap windows
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                mn[h][q] = __reduce_min_sync(0xffffffffu, mn[h][q]);
-                mx[h][q] = __reduce_max_sync(0xffffffffu, mx[h][q]);
-            }
-            if (lane == 0 && mn[h][0] != INT_MAX) {
-                int* b = s.bb[par][h];
-                atomicMin(b + 0, mn[h][0]); atomicMin(b + 1, mn[h][1]); atomicMin(b + 2, mn[h][2]);
-                atomicMax(b + 3, mx[h][0]); atomicMax(b + 4, mx[h][1]); atomicMax(b + 5, mx[h][2]);
-            }
+        for (int q = 0; q < 3; ++q) {
+            mn[q] = __reduce_min_sync(0xffffffffu, mn[q]);
+            mx[q] = __reduce_max_sync(0xffffffffu, mx[q]);
         }
-        __syncthreads();                                           // boxes complete; previous chunk's gathers done
-        // the boxes of chunk c+2 (= chunk c-1's, no longer read) are reset here: chunk c+2's atomics come after
+        if (lane == 0 && mn[0] != INT_MAX) {
+            int* b = s.bb[par];
+            atomicMin(b + 0, mn[0]); atomicMin(b + 1, mn[1]); atomicMin(b + 2, mn[2]);
+            atomicMax(b + 3, mx[0]); atomicMax(b + 4, mx[1]); atomicMax(b + 5, mx[2]);
+        }
+        EDF_TP_MARK(1)
+        __syncthreads();                                           // box complete; previous chunk's gathers done
+        EDF_TP_MARK(2)
+        // the box of chunk c+2 (= chunk c-1's, no longer read) is reset here: chunk c+2's atomics come after
         // the next chunk's barrier
-        if (tid < 16) (&s.bb[par == 0 ? 2 : par - 1][0][0])[tid] = ((tid & 7) < 3) ? INT_MAX : INT_MIN;
-        const int* b0 = s.bb[par][0];
-        const int* b1 = s.bb[par][1];
-        const EdfTileBox full = edf_tile_box<ORDER>(min(b0[0], b1[0]), min(b0[1], b1[1]), min(b0[2], b1[2]),
-                                                    max(b0[3], b1[3]), max(b0[4], b1[4]), max(b0[5], b1[5]));
+        if (tid < 8) s.bb[par == 0 ? 2 : par - 1][tid] = (tid < 3) ? INT_MAX : INT_MIN;
+        const int* b0 = s.bb[par];
+        const EdfTileBox full = edf_tile_box<ORDER>(b0[0], b0[1], b0[2], b0[3], b0[4], b0[5]);
         const int npass = (full.fit || full.empty) ? 1 : 2;
+        if (npass == 2) {
+            // the box outgrows the window (steep field): boxes of the two 2-row halves, reduced from the packed starts
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int hn[3] = {INT_MAX, INT_MAX, INT_MAX}, hx[3] = {INT_MIN, INT_MIN, INT_MIN};
+#pragma unroll
+                for (int u = 2 * h; u < 2 * h + 2; ++u)
+                    if ((actm >> u) & 1u) {
+                        const int stz = z - EDF_SW_PK_BIAS + (int)(pk[u] >> 20), sty = yc0 + u - EDF_SW_PK_BIAS + (int)((pk[u] >> 10) & 1023u);
+                        const int stx = x - EDF_SW_PK_BIAS + (int)(pk[u] & 1023u);
+                        hn[0] = min(hn[0], stz); hn[1] = min(hn[1], sty); hn[2] = min(hn[2], stx);
+                        hx[0] = max(hx[0], stz); hx[1] = max(hx[1], sty); hx[2] = max(hx[2], stx);
+                    }
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    hn[q] = __reduce_min_sync(0xffffffffu, hn[q]);
+                    hx[q] = __reduce_max_sync(0xffffffffu, hx[q]);
+                }
+                if (lane == 0 && hn[0] != INT_MAX) {
+                    int* b = s.hb[h];
+                    atomicMin(b + 0, hn[0]); atomicMin(b + 1, hn[1]); atomicMin(b + 2, hn[2]);
+                    atomicMax(b + 3, hx[0]); atomicMax(b + 4, hx[1]); atomicMax(b + 5, hx[2]);
+                }
+            }
+            __syncthreads();
+        }
         for (int ps = 0; ps < npass; ++ps) {
             EdfTileBox bx_ = full;
-            unsigned rowmask = 0xffu;
+            unsigned rowmask = 0xfu;
             if (npass == 2) {
-                const int* bh = s.bb[par][ps];
+                const int* bh = s.hb[ps];
                 bx_ = edf_tile_box<ORDER>(bh[0], bh[1], bh[2], bh[3], bh[4], bh[5]);
-                rowmask = ps ? 0xf0u : 0x0fu;
+                rowmask = ps ? 0xcu : 0x3u;
                 if (ps) __syncthreads();                           // first pass's gathers done before the window is refilled
             }
             const unsigned am = actm & rowmask;
@@ -327,6 +402,7 @@ edf_tile3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
                 mphase ^= 1u;
                 const bool border = (bx_.wy0 < 0) | (bx_.wy0 + bx_.nyal > leny) | (bx_.wx0 < 0) | (bx_.wx0 + 4 * bx_.nq > lenx);
                 if (border) edf_tile_patch<ORDER>(win, bx_, leny, lenx, tid);
+                EDF_TP_MARK(3)
                 // ---- phase D: gather from the window (inactive lanes read cell 0 and discard)
                 const int slab = bx_.nyal * EDF_TL_PITCH;
                 const int lin0 = ((z - EDF_SW_PK_BIAS - bx_.wz0) * bx_.nyal + (yc0 - EDF_SW_PK_BIAS - bx_.wy0)) * EDF_TL_PITCH +
@@ -339,9 +415,9 @@ edf_tile3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
                     const int off = act ? lin0 + u * EDF_TL_PITCH + (rz * bx_.nyal + ryw) * EDF_TL_PITCH + rx : 0;
                     const float* q0 = win + off;
                     float wzf[NT], wyf[NT], wxf[NT];
-                    edf_bspline_weights_f32<ORDER>(fz[u], wzf);
-                    edf_bspline_weights_f32<ORDER>(fy[u], wyf);
-                    edf_bspline_weights_f32<ORDER>(fx[u], wxf);
+                    edf_tile_weights<ORDER>(fz[u], wzf);
+                    edf_tile_weights<ORDER>(fy[u], wyf);
+                    edf_tile_weights<ORDER>(fx[u], wxf);
                     float acc = 0.f;
 #pragma unroll
                     for (int i = 0; i < NT; ++i) {
@@ -359,17 +435,19 @@ edf_tile3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
                     }
                     if (act) pout[obase_zx + (yc0 + u) * osy] = acc;
                 }
+                EDF_TP_MARK(4)
             } else if (!bx_.empty) {
-                // not even a 4-row half fits the window (very steep field): straight from global memory
-#pragma unroll 1
-                for (int u = 0; u < EDF_TL_MR; ++u) {
-                    if (!((am >> u) & 1u)) continue;
-                    const int stz = z - EDF_SW_PK_BIAS + (int)(pk[u] >> 20), sty = yc0 + u - EDF_SW_PK_BIAS + (int)((pk[u] >> 10) & 1023u);
-                    const int stx = x - EDF_SW_PK_BIAS + (int)(pk[u] & 1023u);
-                    pout[obase_zx + (yc0 + u) * osy] =
-                        edf_swin_direct_gather<ORDER>(pin, stz, sty, stx, fz[u], fy[u], fx[u], lenz, leny, lenx, isz, isy);
-                }
+                // not even a 2-row half fits the window (very steep field): straight from global memory
+#pragma unroll
+                for (int u = 0; u < EDF_TL_MR; ++u)
+                    if ((am >> u) & 1u)
+                        pout[obase_zx + (yc0 + u) * osy] =
+                            edf_tile_direct_voxel<ORDER>(pin, pk[u], fz[u], fy[u], fx[u], z, yc0 + u, x, lenz, leny, lenx, isz, isy);
             }
+        }
+        if (npass == 2) {
+            __syncthreads();                                       // half boxes read by every thread: reset for the next user
+            if (tid < 16) (&s.hb[0][0])[tid] = ((tid & 7) < 3) ? INT_MAX : INT_MIN;
         }
 #pragma unroll
         for (int u = 0; u < EDF_TL_MR; ++u)
@@ -380,8 +458,10 @@ edf_tile3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
             for (int u = 0; u < EDF_TL_MR; ++u)
                 if ((slowm >> u) & 1u) edf_poly_slow_voxel<ORDER, false>(p, L, ii, z, yc0 + u, x);
         }
+        EDF_TP_MARK(5)
         par = par == 2 ? 0 : par + 1;
     }
+    EDF_TP_FLUSH
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -445,7 +525,7 @@ static void edf_tile_grid(const EdfParams& p, EdfFastLaunch& L, unsigned& ncta)
 {
     const uint64_t gx = (uint64_t)((p.odim[2] + EDF_PL_TX - 1) / EDF_PL_TX);
     const uint64_t gz = (uint64_t)((p.odim[0] + EDF_PL_G - 1) / EDF_PL_G);
-    unsigned ry = EDF_PL_RY;
+    unsigned ry = 16;
     static int env_ry = -1;                                        // EDF_TILE_ROWS=8/16/32/64: rows per CTA (A/B runs)
     if (env_ry < 0) { const char* e = getenv("EDF_TILE_ROWS"); env_ry = (e && *e) ? atoi(e) : 0; }
     if (env_ry == 8 || env_ry == 16 || env_ry == 32 || env_ry == 64) ry = (unsigned)env_ry;

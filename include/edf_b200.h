@@ -142,6 +142,9 @@ uint64_t edf_launch_count(void);
 /* Name of the kernel family chosen by the most recent edf_deform_grid* call on
  * this thread ("generic", "fast3d_o3", ...). */
 const char* edf_last_kernel(void);
+/* Debug/measurement: cycles per phase of the staged-window kernels, summed over warps, in builds compiled with
+ * -DEDF_TILE_PROFILE (all zero otherwise); out16[15] = number of warps. Reads and resets. Synchronises. */
+int edf_debug_tile_profile(uint64_t* out16);
 
 #ifdef __cplusplus
 }
