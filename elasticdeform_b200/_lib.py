@@ -68,7 +68,7 @@ class EdfProblem(ctypes.Structure):
     ]
 
 
-# every symbol include/edf_b200.h declares (checked by tests/test_abi.py)
+# every symbol include/edf_b200.h declares (checked by tests/test_host_api.py)
 EXPORTED_SYMBOLS = (
     "edf_deform_grid", "edf_deform_grid_grad", "edf_deform_grid_batch",
     "edf_spline_filter1d", "edf_spline_filter1d_grad", "edf_last_error",

@@ -17,6 +17,9 @@
 #include "edf_swin.cuh"
 #include "edf_poly.cuh"
 #include "edf_tile.cuh"
+#ifdef EDF_WITH_PIPE
+#include "experimental/edf_pipe.cuh"   // producer / consumer pipeline (measured slower than the staged-window kernels)
+#endif
 
 // ----------------------------------------------------------------------------
 // error plumbing

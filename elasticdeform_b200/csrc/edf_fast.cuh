@@ -168,15 +168,70 @@ __device__ __forceinline__ void edf_fast_chunk_setup(EdfFastSmem<NAXIS>& s, int 
     }
 }
 
-// exact reference-order displacement, kept out of line so that its index tables do not
-// inflate the register footprint of the hot loop (it runs for ~1 voxel in 10^6)
+// Exact reference-order displacement (deform.c:650-758) of one voxel, out of line: it runs for the ~1 voxel in 10^5
+// that sits next to a rounding threshold -- but a warp that hits one waits for it, and its CTA with it, so the
+// latency of this routine is on the critical path of every fast kernel (ncu, round 2: 400 warp-level calls of the
+// generic form -- a 64-iteration loop with local-memory index tables and a 13-way dtype switch per tap, ~10^5
+// cycles each -- accounted for a third of the stall samples of the order-0 forward kernel).  For float64 / float32
+// control points (what the fast kernels accept) the taps are fully unrolled: the loads are independent, the
+// products ((D * w_0) * w_1) * w_2 and the running sum keep the reference's order and rounding (no FMA).
+template <int NAXIS, typename TD>
+__device__ __forceinline__ void edf_displacement_exact_unrolled(const EdfParams& p, const int* o, double* dd)
+{
+    double dw[NAXIS][4];
+    int64_t doff[NAXIS][4];
+#pragma unroll
+    for (int a = 0; a < NAXIS; ++a) {
+        const double cp = edf_control_pos(p, a, (int64_t)o[a]);
+        const int64_t start = (int64_t)floor(cp) - 1;
+        edf_bspline_weights(cp, 3, dw[a]);
+        const bool edge = start < 0 || start + 3 >= p.ncp[a];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            int64_t idx = start + l;
+            if (edge) idx = edf_mirror_index(idx, p.ncp[a]);
+            doff[a][l] = idx * p.dstr[a + 1];
+        }
+    }
+#pragma unroll 1
+    for (int h = 0; h < NAXIS; ++h) {
+        const char* bh = p.disp + p.dstr[0] * h;
+        double sum = 0.0;
+        if (NAXIS == 3) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double c[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) c[q] = (double)*(const TD*)(bh + doff[0][i] + doff[1][q >> 2] + doff[2][q & 3]);
+#pragma unroll
+                for (int q = 0; q < 16; ++q)
+                    sum = xadd(sum, xmul(xmul(xmul(c[q], dw[0][i]), dw[1][q >> 2]), dw[2][q & 3]));
+            }
+        } else {
+            double c[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) c[q] = (double)*(const TD*)(bh + doff[0][q >> 2] + doff[1][q & 3]);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) sum = xadd(sum, xmul(xmul(c[q], dw[0][q >> 2]), dw[1][q & 3]));
+        }
+        dd[h] = sum;
+    }
+}
+
 template <int NAXIS>
 __device__ __noinline__ void edf_displacement_exact_cold(const EdfParams& p, const int* o, double* dd)
 {
-    int64_t o64[NAXIS];
+    static_assert(NAXIS == 2 || NAXIS == 3, "fast kernels: 2-D and 3-D");
+    if (p.ddtype == EDF_F64) {
+        edf_displacement_exact_unrolled<NAXIS, double>(p, o, dd);
+    } else if (p.ddtype == EDF_F32) {
+        edf_displacement_exact_unrolled<NAXIS, float>(p, o, dd);
+    } else {
+        int64_t o64[NAXIS];
 #pragma unroll
-    for (int h = 0; h < NAXIS; ++h) o64[h] = o[h];
-    edf_displacement_exact<NAXIS>(p, o64, dd);
+        for (int h = 0; h < NAXIS; ++h) o64[h] = o[h];
+        edf_displacement_exact<NAXIS>(p, o64, dd);
+    }
 }
 
 // un-mapped source coordinates in[h] of one voxel, with the exact-order re-evaluation
@@ -600,6 +655,16 @@ static int edf_poly_direct_launch(int order, cudaStream_t st, const EdfParams& p
 // staged-window kernels of round 2 (edf_tile.cuh): tensor-map TMA staging, polynomial coordinates
 static bool edf_tile_fwd_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii);
 static int edf_tile_launch_fwd(int order, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii);
+static bool edf_tile_env()                              // EDF_TILE=1: the tensor-map TMA forward kernel instead of the bulk-copy one
+{                                                       //   (A/B runs: 0.56 vs 0.47 ms at order 3, 0.34 vs 0.32 ms at order 2 on 256^3)
+    static std::atomic<int> v{-1};
+    int x = v.load(std::memory_order_relaxed);
+    if (x < 0) { const char* e = getenv("EDF_TILE"); x = (e && *e && *e != '0') ? 1 : 0; v.store(x, std::memory_order_relaxed); }
+    return x != 0;
+}
+// producer / consumer pipeline of staged windows (edf_pipe.cuh): forward gather, orders 0-3, 'constant' mode
+static bool edf_pipe_fwd_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii);
+static int edf_pipe_launch_fwd(int order, cudaStream_t st, const EdfParams& p, const EdfFastLaunch& L, int ii);
 
 // Tries to run (part of) the problem on the specialised kernels.
 //   *handled_mask receives the inputs that were processed (the caller runs the generic
@@ -647,9 +712,26 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
             // caller hints a steep field (boxes that outgrow the window -> the round-1 kernels are faster there)
             int rcs = -2;
             const bool steep = (flags & EDF_FLAG_STEEP) != 0;
+            // An affine map that magnifies by more than ~3.6x per axis sends > 48 output voxels to every input cell: the
+            // 32-bit fixed-point cells of the gradient windows (headroom ~128 voxels' worth of mass) are not used then
+            // (the staged-window kernel also checks the multiplicity per chunk on the device, for what the displacement adds)
+            bool dense_affine = false;
+            if (p.gradient && p.has_affine) {
+                const double* A = p.affine;
+                const double det = A[0] * (A[5] * A[10] - A[6] * A[9]) - A[1] * (A[4] * A[10] - A[6] * A[8]) + A[2] * (A[4] * A[9] - A[5] * A[8]);
+                dense_affine = !(fabs(det) >= 1.0 / 48.0);
+            }
             const int ord = p.inp[ii].order;
-            bool poly = false, tile = false;
-            if (!p.gradient && ord <= 1 && !(flags & EDF_FLAG_STAGED_FWD) && edf_poly_direct_eligible(p, L, ii)) {
+            bool poly = false, tile = false, pipe = false;
+#ifdef EDF_WITH_PIPE
+            if (!p.gradient && windows && !steep && !(flags & EDF_FLAG_STAGED_FWD) && edf_pipe_fwd_eligible(p, L, ii)) {
+                rcs = edf_pipe_launch_fwd(ord, st, p, L, ii);
+                pipe = rcs == 0;
+            }
+#endif
+            if (rcs != -2) {
+                // launched (or failed) above
+            } else if (!p.gradient && ord <= 1 && !(flags & EDF_FLAG_STAGED_FWD) && edf_poly_direct_eligible(p, L, ii)) {
                 // orders 0 / 1, 'constant' mode: polynomial coordinates, direct gather
                 rcs = edf_poly_direct_launch(ord, st, p, L, ii);
                 poly = rcs == 0;
@@ -659,24 +741,26 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
                 const bool big = (uint64_t)p.odim[0] * (uint64_t)p.odim[1] * (uint64_t)p.odim[2] >= EDF_SWIN_FWD_MIN_VOXELS;
                 const bool want = (flags & EDF_FLAG_STAGED_FWD) || edf_swin_fwd_env() ||
                                   (!steep && big && ord >= 2 && ord <= edf_swin_max_fwd_order());
-                if (want && edf_tile_fwd_eligible(p, L, ii)) {
+                if (want && edf_tile_env() && edf_tile_fwd_eligible(p, L, ii)) {
                     rcs = edf_tile_launch_fwd(ord, st, p, L, ii);
                     tile = rcs == 0;
                 }
                 if (rcs == -2 && want && edf_swin_eligible(p, L, ii)) rcs = edf_swin_launch(ord, 0, st, p, L, ii);
-            } else if (windows && p.gradient && !(flags & EDF_FLAG_FIXED_WINDOW) &&
+            } else if (windows && !dense_affine && p.gradient && !(flags & EDF_FLAG_FIXED_WINDOW) &&
                        ((flags & EDF_FLAG_STAGED_ALL) || !(steep && ord >= 2))) {
                 if (edf_swin_grad_eligible(p, L, ii, (flags & EDF_FLAG_STAGED_ALL) != 0))
                     rcs = edf_swin_launch(ord, 1, st, p, L, ii);
             }
             if (rcs == -1) return -1;
-            if (rcs == 0 && poly) {
+            if (rcs == 0 && pipe) {
+                *name = "pipe3d_f32";
+            } else if (rcs == 0 && poly) {
                 *name = "poly3d_f32_direct";
             } else if (rcs == 0 && tile) {
                 *name = p.gradient ? "tile3d_f32_grad" : "tile3d_f32";
             } else if (rcs == 0) {
                 *name = p.gradient ? "swin3d_f32_grad" : "swin3d_f32";
-            } else if (windows && p.gradient && edf_gradwin_eligible(p)) {
+            } else if (windows && !dense_affine && p.gradient && edf_gradwin_eligible(p)) {
                 const int rcw = edf_lean_launch_gradwin(p.inp[ii].order, st, p, L, ii);
                 if (rcw < 0) return -1;
                 *name = rcw == 2 ? "lean3d_f32_gradwin_tma" : "lean3d_f32_gradwin";

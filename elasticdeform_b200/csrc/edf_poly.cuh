@@ -34,6 +34,7 @@ struct EdfPolyTables {
     int    jy[EDF_PL_RY];          // first control row of each row's window (floor(cp) - 1)
     int    sz[EDF_PL_G];
     int    sx[EDF_PL_TX];
+    double rrat;                   // (I_y - 1) / (P_y - 1): rows per control interval
 };
 
 // CTA prologue: control tables of the tile (x0.., y0.., z0..); ends with a CTA barrier
@@ -53,6 +54,8 @@ __device__ __forceinline__ void edf_poly_tables(const EdfParams& p, EdfPolyTable
     } else if (tid < EDF_PL_TX + EDF_PL_RY + EDF_PL_G) {
         const int t = tid - EDF_PL_TX - EDF_PL_RY;
         edf_fast_ctrl_entry(p, 0, min((int64_t)(z0 + t), p.odim[0] - 1), s.wz[t], &s.sz[t]);
+    } else if (tid == EDF_PL_TX + EDF_PL_RY + EDF_PL_G) {
+        s.rrat = xdiv(p.idim_m1[1], (double)(p.ncp[1] > 1 ? p.ncp[1] - 1 : 1));
     }
     __syncthreads();
 }
@@ -60,7 +63,8 @@ __device__ __forceinline__ void edf_poly_tables(const EdfParams& p, EdfPolyTable
 // Rebuild the polynomial coefficients of this thread's column for the control interval whose window starts at
 // control row j0.  Warp-collective (all 32 lanes).  Returns the warp's gate: false when every control
 // coefficient the warp touches is zero (then a == 0 exactly).
-__device__ __forceinline__ bool edf_poly_build(const EdfParams& p, EdfPolyTables& s, int g, int lane, int j0, double* a /*[3][4]*/, int tw = -1)
+template <class Tab>
+__device__ __forceinline__ bool edf_poly_build(const EdfParams& p, Tab& s, int g, int lane, int j0, double* a /*[3][4]*/, int tw = -1)
 {
     static_assert(EDF_PL_NC == 8, "lane -> (control row, control column) mapping");
     if (tw < 0) tw = g;                                            // table slot of this warp
@@ -135,6 +139,167 @@ __device__ __forceinline__ void edf_poly_eval(const double* a, double u, double&
     dx = fma(fma(fma(a[11], u, a[10]), u, a[9]), u, a[8]);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Fixed-point source coordinates.  The row's own index, the crop offset and the affine map (deform.c:771-781)
+// are folded into the column's polynomial, and so is the constant 1.5 * 2^29: the last FMA of the Horner form
+// then rounds the SOURCE COORDINATE c to a multiple of 2^-23, and floor / fractional offset / range tests are
+// integer operations on the two words of the result -- no conversion instructions, no fp64 compares:
+//     T = c + 1.5*2^29   ->   floor(c) = bits [23,55) of T - const,    frac(c) = (lo & 0x7fffff) * 2^-23.
+// Even orders fold another 0.5 in (their window start is floor(c + 0.5), deform.c:784-788).  The quantisation
+// moves a coordinate by < 1.2e-7; voxels within 2^-21 of a threshold (integer coordinates for odd orders, integer
+// and half-integer ones for even orders) are flagged `slow` and redone in the reference order, so every discrete
+// decision still equals the reference's.
+// ---------------------------------------------------------------------------------------------------------
+#define EDF_PP_FBITS 23
+#define EDF_PP_MAGIC 805306368.0   // 1.5 * 2^29: ulp 2^-23
+#define EDF_PP_HI0 0x41C00000u     // high word of 2^29 (exponent 1052)
+#define EDF_PP_FLBIAS 0x90000000u  // bits [23,55) of the pattern of EDF_PP_MAGIC
+#define EDF_PP_NEAR 4.7683716e-7f  // 2^-21: four steps of the 2^-23 grid (quantisation: half a step each for the fold and the last FMA)
+
+// a[h*4 + k] (displacement along axis h as a cubic in u, edf_poly_build) -> out[h*4 + k]: source coordinate
+// (+ 0.5 for even orders) + 1.5*2^29 of the column (z, x) as a cubic in u, for the control interval whose window
+// starts at control row j0.  r = (I_y - 1) / (P_y - 1): y + off_y = (j0 + 1 + u) * r  (cp = (P-1)(y+off)/(I-1), deform.c:655)
+template <int ORDER>
+__device__ __forceinline__ void edf_poly_fold(const EdfParams& p, const double* a, double r, int j0, int z, int x, double* out)
+{
+    const double yj = xmul((double)(j0 + 1), r);
+    const double half = (ORDER & 1) ? 0.0 : 0.5;
+    if (p.has_affine) {
+        const double yo = xsub(yj, p.ooff_d[1]);                 // output row index at u = 0
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+            const double* A = p.affine + h * 4;
+            const double c = fma(A[0], (double)z, fma(A[1], yo, fma(A[2], (double)x, A[3]))) + p.ooff_d[h];
+            out[h * 4 + 0] = ((a[h * 4 + 0] + c) + half) + EDF_PP_MAGIC;
+            out[h * 4 + 1] = fma(A[1], r, a[h * 4 + 1]);
+            out[h * 4 + 2] = a[h * 4 + 2];
+            out[h * 4 + 3] = a[h * 4 + 3];
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+            const double c = (h == 0) ? xadd((double)z, p.ooff_d[0]) : (h == 1) ? yj : xadd((double)x, p.ooff_d[2]);
+            out[h * 4 + 0] = ((a[h * 4 + 0] + c) + half) + EDF_PP_MAGIC;
+            out[h * 4 + 1] = (h == 1) ? a[h * 4 + 1] + r : a[h * 4 + 1];
+            out[h * 4 + 2] = a[h * 4 + 2];
+            out[h * 4 + 3] = a[h * 4 + 3];
+        }
+    }
+}
+
+// Source coordinates of one voxel from the folded polynomial (see the header): window starts, centred fractional
+// offsets e = frac - 0.5, strict in-range flag and `slow` (redo in the reference order).
+struct EdfPipeVoxel {
+    int stz, sty, stx;
+    float ez, ey, ex;
+    bool inr, slow;
+};
+template <int ORDER>
+__device__ __forceinline__ void edf_pipe_coords(const double* a, double u, bool gate, int lenz, int leny, int lenx,
+                                                unsigned rngz, unsigned rngy, unsigned rngx, EdfPipeVoxel& v)
+{
+    const double Tz = fma(fma(fma(a[3], u, a[2]), u, a[1]), u, a[0]);
+    const double Ty = fma(fma(fma(a[7], u, a[6]), u, a[5]), u, a[4]);
+    const double Tx = fma(fma(fma(a[11], u, a[10]), u, a[9]), u, a[8]);
+    const unsigned loz = (unsigned)__double2loint(Tz), hiz = (unsigned)__double2hiint(Tz);
+    const unsigned loy = (unsigned)__double2loint(Ty), hiy = (unsigned)__double2hiint(Ty);
+    const unsigned lox = (unsigned)__double2loint(Tx), hix = (unsigned)__double2hiint(Tx);
+    // |c| < 2^28 (and not NaN): the exponent field of all three results is that of 2^29
+    const bool expok = (((hiz - EDF_PP_HI0) | (hiy - EDF_PP_HI0) | (hix - EDF_PP_HI0)) < 0x00100000u);
+    const int flz = (int)(__funnelshift_r(loz, hiz, EDF_PP_FBITS) - EDF_PP_FLBIAS);
+    const int fly = (int)(__funnelshift_r(loy, hiy, EDF_PP_FBITS) - EDF_PP_FLBIAS);
+    const int flx = (int)(__funnelshift_r(lox, hix, EDF_PP_FBITS) - EDF_PP_FLBIAS);
+    const unsigned gqz = loz & 0x7fffffu, gqy = loy & 0x7fffffu, gqx = lox & 0x7fffffu;
+    v.ez = __uint_as_float(gqz | 0x3f800000u) - 1.5f;             // exact
+    v.ey = __uint_as_float(gqy | 0x3f800000u) - 1.5f;
+    v.ex = __uint_as_float(gqx | 0x3f800000u) - 1.5f;
+    bool near;
+    if (ORDER & 1) {
+        v.inr = ((unsigned)flz <= rngz) & ((unsigned)fly <= rngy) & ((unsigned)flx <= rngx);
+        near = !(fmaxf(fmaxf(fabsf(v.ez), fabsf(v.ey)), fabsf(v.ex)) < 0.5f - EDF_PP_NEAR);
+    } else {
+        // T holds c + 0.5: floor(2c + 1) = 2 * floor + (frac >= 0.5); c in [0, len-1] <=> 1 <= that <= 2 len - 1
+        const unsigned hz = 2u * (unsigned)flz + (gqz >> 22), hy = 2u * (unsigned)fly + (gqy >> 22), hx = 2u * (unsigned)flx + (gqx >> 22);
+        v.inr = (hz - 1u <= rngz) & (hy - 1u <= rngy) & (hx - 1u <= rngx);
+        const float qz = fabsf(fabsf(v.ez) - 0.25f), qy = fabsf(fabsf(v.ey) - 0.25f), qx = fabsf(fabsf(v.ex) - 0.25f);
+        near = !(fmaxf(fmaxf(qz, qy), qx) < 0.25f - EDF_PP_NEAR);
+    }
+    v.slow = (gate & near) | !expok;
+    if (!v.inr & !v.slow) {
+        // exactly on the upper limit (un-gated integer coordinates: identity maps): in range in the reference
+        const unsigned k = (ORDER & 1) ? 0u : 0x400000u;
+        v.slow = ((flz == lenz - 1) & (gqz == k)) | ((fly == leny - 1) & (gqy == k)) | ((flx == lenx - 1) & (gqx == k));
+    }
+    v.stz = flz - ORDER / 2; v.sty = fly - ORDER / 2; v.stx = flx - ORDER / 2;
+}
+
+// Lean form for the direct kernels: the same fixed-point coordinates with the flags folded into one code,
+//     >= 0 : element offset of the first tap (in range, taps inside the volume -- orders 0 / 1, 'constant' mode)
+//     -1   : takes the constant value        -2 : redo in the reference order (`slow`)
+// limlo*: low word of the pattern of (len - 1 [+ 0.5]) + 1.5*2^29 -- a coordinate exactly on the upper limit is in
+// range in the reference (deform.c:84-86) although its floor fails the strict test; a chance match of the low word
+// alone only sends a voxel to the exact routine.
+template <int ORDER>
+__device__ __forceinline__ int edf_fx_code(const double* a, double u, bool gate, unsigned rngz, unsigned rngy, unsigned rngx,
+                                           unsigned limloz, unsigned limloy, unsigned limlox, int isz, int isy,
+                                           float& ez, float& ey, float& ex)
+{
+    static_assert(ORDER == 0 || ORDER == 1, "taps inside the volume whenever the coordinate is strictly in range");
+    const double Tz = fma(fma(fma(a[3], u, a[2]), u, a[1]), u, a[0]);
+    const double Ty = fma(fma(fma(a[7], u, a[6]), u, a[5]), u, a[4]);
+    const double Tx = fma(fma(fma(a[11], u, a[10]), u, a[9]), u, a[8]);
+    const unsigned loz = (unsigned)__double2loint(Tz), hiz = (unsigned)__double2hiint(Tz);
+    const unsigned loy = (unsigned)__double2loint(Ty), hiy = (unsigned)__double2hiint(Ty);
+    const unsigned lox = (unsigned)__double2loint(Tx), hix = (unsigned)__double2hiint(Tx);
+    const unsigned bad = ((hiz - EDF_PP_HI0) | (hiy - EDF_PP_HI0) | (hix - EDF_PP_HI0)) >> 20;     // != 0: |c| >= 2^28 or NaN
+    const unsigned flz = __funnelshift_r(loz, hiz, EDF_PP_FBITS) - EDF_PP_FLBIAS;
+    const unsigned fly = __funnelshift_r(loy, hiy, EDF_PP_FBITS) - EDF_PP_FLBIAS;
+    const unsigned flx = __funnelshift_r(lox, hix, EDF_PP_FBITS) - EDF_PP_FLBIAS;
+    ez = __uint_as_float((loz & 0x7fffffu) | 0x3f800000u) - 1.5f;
+    ey = __uint_as_float((loy & 0x7fffffu) | 0x3f800000u) - 1.5f;
+    ex = __uint_as_float((lox & 0x7fffffu) | 0x3f800000u) - 1.5f;
+    bool inr, near;
+    if (ORDER & 1) {
+        inr = (flz <= rngz) & (fly <= rngy) & (flx <= rngx);
+        near = !(fmaxf(fmaxf(fabsf(ez), fabsf(ey)), fabsf(ex)) < 0.5f - EDF_PP_NEAR);
+    } else {
+        const unsigned hz = __funnelshift_r(loz, hiz, EDF_PP_FBITS - 1) - 2u * EDF_PP_FLBIAS - 1u;      // floor(2c + 1) - 1
+        const unsigned hy = __funnelshift_r(loy, hiy, EDF_PP_FBITS - 1) - 2u * EDF_PP_FLBIAS - 1u;
+        const unsigned hx = __funnelshift_r(lox, hix, EDF_PP_FBITS - 1) - 2u * EDF_PP_FLBIAS - 1u;
+        inr = (hz <= rngz) & (hy <= rngy) & (hx <= rngx);
+        const float qz = fabsf(fabsf(ez) - 0.25f), qy = fabsf(fabsf(ey) - 0.25f), qx = fabsf(fabsf(ex) - 0.25f);
+        near = !(fmaxf(fmaxf(qz, qy), qx) < 0.25f - EDF_PP_NEAR);
+    }
+    const bool slow = (gate & near) | (bad != 0u) | (loz == limloz) | (loy == limloy) | (lox == limlox);
+    const int off = (int)flz * isz + (int)fly * isy + (int)flx;
+    return slow ? -2 : (inr ? off : -1);
+}
+
+// interpolation weights from e = frac - 0.5 (odd orders, frac in [0,1)) or e = frac (even orders, in [-0.5,0.5))
+template <int ORDER>
+__device__ __forceinline__ void edf_pipe_weights(float e, float* w)
+{
+    if (ORDER == 1) {
+        w[0] = 0.5f - e;
+        w[1] = 0.5f + e;
+    } else if (ORDER == 2) {
+        const float a = 0.5f - e, b = 0.5f + e;
+        w[0] = 0.5f * a * a;
+        w[1] = fmaf(-e, e, 0.75f);
+        w[2] = 0.5f * b * b;
+    } else if (ORDER == 3) {
+        // (0.5 -+ e)^3 / 6 and 2/3 - t^2 + t^3/2 at t = 0.5 +- e, split into even and odd parts of e
+        const float e2 = e * e;
+        const float A = fmaf(e2, 0.25f, 1.0f / 48.0f);
+        const float B = e * fmaf(e2, 1.0f / 6.0f, 0.125f);
+        const float C = fmaf(e2, -0.25f, 23.0f / 48.0f);
+        const float D = e * fmaf(e2, -0.5f, 0.625f);
+        w[0] = A - B; w[3] = A + B;
+        w[1] = C - D; w[2] = C + D;
+    }
+}
+
 // rare voxel (next to a rounding / boundary threshold, edge of the volume): exact reference-order coordinates,
 // then the general single-voxel routine (any mode, mirrored edge taps)
 template <int ORDER, bool GRAD>
@@ -170,23 +335,29 @@ edf_poly3d_fwd_direct_kernel(const __grid_constant__ EdfParams p, const __grid_c
     const int odz = (int)p.odim[0], ody = (int)p.odim[1], odx = (int)p.odim[2];
     if (z >= odz) return;                                          // whole warp (no CTA barrier below)
     const bool tok = x < odx;
+    const int xc = min(x, odx - 1);
     const EdfInputDesc& d = p.inp[ii];
     const float* __restrict__ pin = (const float*)d.in;
     float* __restrict__ pout = (float*)d.out;
     const int lenz = (int)p.idim[0], leny = (int)p.idim[1], lenx = (int)p.idim[2];
-    const double limz = p.idim_m1[0], limy = p.idim_m1[1], limx = p.idim_m1[2];
+    // strict in-range tests on the fixed-point floor (edf_pipe_coords); in 'constant' mode an in-range voxel that is
+    // not next to a threshold has all its taps inside the volume at orders 0 and 1: no edge case
+    const unsigned rngz = (ORDER & 1) ? (unsigned)(lenz - 2) : (unsigned)(2 * lenz - 3);
+    const unsigned rngy = (ORDER & 1) ? (unsigned)(leny - 2) : (unsigned)(2 * leny - 3);
+    const unsigned rngx = (ORDER & 1) ? (unsigned)(lenx - 2) : (unsigned)(2 * lenx - 3);
     const int isz = L.istr_e[ii][0], isy = L.istr_e[ii][1];
     const int osy = L.ostr_e[ii][1];
-    const int obase_zx = z * L.ostr_e[ii][0] + x * L.ostr_e[ii][2];      // element offsets fit 32 bits (host-checked)
+    const int obase_zx = z * L.ostr_e[ii][0] + xc * L.ostr_e[ii][2];     // element offsets fit 32 bits (host-checked)
     const float cvalf = __uint_as_float((uint32_t)L.cval_bits[ii]);
-    const double bz = xadd((double)z, p.ooff_d[0]);
-    const double bx = xadd((double)x, p.ooff_d[2]);
     const int nrow = min(ry, ody - y0);
+    const double rrat = s.rrat;
+    const unsigned hlf = (ORDER & 1) ? 0u : 0x400000u;
+    const unsigned limloz = ((unsigned)(lenz - 1) << EDF_PP_FBITS) + hlf, limloy = ((unsigned)(leny - 1) << EDF_PP_FBITS) + hlf,
+                   limlox = ((unsigned)(lenx - 1) << EDF_PP_FBITS) + hlf;
 
     double a[12];
     int jcur = INT_MIN;
     bool gate = false;
-    double by = xadd((double)y0, p.ooff_d[1]);                     // exact: integers
 
     int nb = U;
 #pragma unroll 1
@@ -194,58 +365,33 @@ edf_poly3d_fwd_direct_kernel(const __grid_constant__ EdfParams p, const __grid_c
         // rows of this iteration: up to U, all inside one control interval (the only call site of the rebuild)
         const int jr = s.jy[m0];
         if (jr != jcur) {                                          // warp-uniform
-            gate = edf_poly_build(p, s, g, lane, jr, a);
+            double a0[12];
+            gate = edf_poly_build(p, s, g, lane, jr, a0) | (p.has_affine != 0);
+            edf_poly_fold<ORDER>(p, a0, rrat, jr, z, xc, a);
             jcur = jr;
         }
         nb = min(U, nrow - m0);
 #pragma unroll
         for (int u = U - 1; u >= 1; --u)
             if (u < nb && s.jy[m0 + u] != jr) nb = u;
-        int st[U][3];
-        float fr[U][3];
-        bool inr[U], slow[U];
+        int e[U];
+        float fz[U], fy[U], fx[U];
+        int emin = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int m = m0 + min(u, nb - 1);
-            double dz, dy, dx;
-            edf_poly_eval(a, s.u[m], dz, dy, dx);
-            const double cz = xadd(bz, dz);
-            const double cy = xadd(xadd(by, (double)(m - m0)), dy);
-            const double cx = xadd(bx, dx);
-            inr[u] = (cz >= 0.0) & (cz <= limz) & (cy >= 0.0) & (cy <= limy) & (cx >= 0.0) & (cx <= limx);
-            edf_floor_split<ORDER>(cz, st[u][0], fr[u][0]);
-            edf_floor_split<ORDER>(cy, st[u][1], fr[u][1]);
-            edf_floor_split<ORDER>(cx, st[u][2], fr[u][2]);
-            // next to a threshold (odd orders: the integers; even orders: the half-integers, and the integers 0 and
-            // len-1 of the range test): redone in the reference order.  |c| >= 2^31 never passes the range test.
-            float dmax;
-            if (ORDER & 1) {
-                dmax = fmaxf(fmaxf(fabsf(fr[u][0] - 0.5f), fabsf(fr[u][1] - 0.5f)), fabsf(fr[u][2] - 0.5f));
-            } else {
-                const float q0 = fabsf(fabsf(fr[u][0]) - 0.25f), q1 = fabsf(fabsf(fr[u][1]) - 0.25f), q2 = fabsf(fabsf(fr[u][2]) - 0.25f);
-                dmax = 2.0f * fmaxf(fmaxf(q0, q1), q2);            // |fr| near 0 or near 0.5  <=>  | |fr| - 0.25 | near 0.25
-            }
-            const bool danger = gate & !(dmax < 0.5f - EDF_LEAN_EPSF);      // NaN -> danger
-            // taps across the border of the volume (only exact-integer coordinates get here in 'constant' mode)
-            const bool edge = ((unsigned)st[u][0] > (unsigned)(lenz - 1 - ORDER)) | ((unsigned)st[u][1] > (unsigned)(leny - 1 - ORDER)) |
-                              ((unsigned)st[u][2] > (unsigned)(lenx - 1 - ORDER));
-            const bool valid = tok & (u < nb);
-            slow[u] = valid & (danger | (inr[u] & edge));
-            inr[u] = inr[u] & !edge;
+            e[u] = edf_fx_code<ORDER>(a, s.u[m], gate, rngz, rngy, rngx, limloz, limloy, limlox, isz, isy, fz[u], fy[u], fx[u]);
+            emin = min(emin, e[u]);
         }
         float t[U];
         if (ORDER == 0) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int e = inr[u] ? st[u][0] * isz + st[u][1] * isy + st[u][2] : 0;
-                t[u] = __ldg(pin + e);
-            }
+            for (int u = 0; u < U; ++u) t[u] = __ldg(pin + max(e[u], 0));
         } else {
             float v[U][8];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int e = inr[u] ? st[u][0] * isz + st[u][1] * isy + st[u][2] : 0;
-                const float* b0 = pin + e;
+                const float* b0 = pin + max(e[u], 0);
                 const float* b1 = b0 + isy;
                 const float* b2 = b0 + isz;
                 const float* b3 = b2 + isy;
@@ -256,32 +402,27 @@ edf_poly3d_fwd_direct_kernel(const __grid_constant__ EdfParams p, const __grid_c
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                float wz[2], wy[2], wx[2];
-                edf_bspline_weights_f32<1>(fr[u][0], wz);
-                edf_bspline_weights_f32<1>(fr[u][1], wy);
-                edf_bspline_weights_f32<1>(fr[u][2], wx);
-                // same association as the other float32 kernels: x, then y, then z
-                const float r00 = fmaf(v[u][1], wx[1], v[u][0] * wx[0]);
-                const float r01 = fmaf(v[u][3], wx[1], v[u][2] * wx[0]);
-                const float r10 = fmaf(v[u][5], wx[1], v[u][4] * wx[0]);
-                const float r11 = fmaf(v[u][7], wx[1], v[u][6] * wx[0]);
-                const float p0 = fmaf(r01, wy[1], r00 * wy[0]);
-                const float p1 = fmaf(r11, wy[1], r10 * wy[0]);
-                t[u] = fmaf(p1, wz[1], p0 * wz[0]);
+                // weights 0.5 -+ e from the centred offsets; x, then y, then z as in the other float32 kernels
+                const float wx0 = 0.5f - fx[u], wx1 = 0.5f + fx[u];
+                const float wy0 = 0.5f - fy[u], wy1 = 0.5f + fy[u];
+                const float wz0 = 0.5f - fz[u], wz1 = 0.5f + fz[u];
+                const float r00 = fmaf(v[u][1], wx1, v[u][0] * wx0);
+                const float r01 = fmaf(v[u][3], wx1, v[u][2] * wx0);
+                const float r10 = fmaf(v[u][5], wx1, v[u][4] * wx0);
+                const float r11 = fmaf(v[u][7], wx1, v[u][6] * wx0);
+                const float p0 = fmaf(r01, wy1, r00 * wy0);
+                const float p1 = fmaf(r11, wy1, r10 * wy0);
+                t[u] = fmaf(p1, wz1, p0 * wz0);
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (tok & (u < nb)) pout[obase_zx + (y0 + m0 + u) * osy] = inr[u] ? t[u] : cvalf;
-        bool anyslow = false;
-#pragma unroll
-        for (int u = 0; u < U; ++u) anyslow |= slow[u];
-        if (anyslow) {
+            if (tok & (u < nb) & (e[u] != -2)) pout[obase_zx + (y0 + m0 + u) * osy] = e[u] >= 0 ? t[u] : cvalf;
+        if ((emin == -2) & tok) {
 #pragma unroll 1
             for (int u = 0; u < U; ++u)
-                if (slow[u]) edf_poly_slow_voxel<ORDER, false>(p, L, ii, z, y0 + m0 + u, x);
+                if ((e[u] == -2) & (u < nb)) edf_poly_slow_voxel<ORDER, false>(p, L, ii, z, y0 + m0 + u, x);
         }
-        by = xadd(by, (double)nb);
     }
 }
 
@@ -290,7 +431,10 @@ static bool edf_poly_direct_eligible(const EdfParams& p, const EdfFastLaunch& L,
 {
     if (!edf_lean_eligible(p, L, ii)) return false;
     const EdfInputDesc& d = p.inp[ii];
-    if (d.mode != EDF_MODE_CONSTANT || d.order > 1 || p.has_affine) return false;
+    if (d.mode != EDF_MODE_CONSTANT || d.order > 1) return false;
+    if (p.ncp[1] < 2) return false;                                // the row index is folded into the polynomial in u
+    for (int a = 0; a < 3; ++a)
+        if (p.idim[a] > (1 << 26) || p.odim[a] > (1 << 26)) return false;   // fixed-point coordinates: |c| < 2^28
     if (!edf_fast_ctrl_span_ok(p, 2, EDF_PL_TX, EDF_PL_NC)) return false;
     // a control interval should span several rows, or the polynomial is rebuilt all the time
     if ((p.idim[1] - 1) < 8 * (p.ncp[1] - 1)) return false;

@@ -797,6 +797,15 @@ def _is_array(x):
     return isinstance(x, numpy.ndarray) or _is_tensor(x)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Argument normalisers.  These follow elasticdeform/deform_grid.py:295-439 of the reference (BSD licence,
+# (c) 2018 Gijs van Tulder -- see LICENSE, "Third-party notices") statement by statement ON PURPOSE: the
+# drop-in contract is "same names, defaults, exception types and messages", and these few lines of host-side
+# argument checking ARE that contract.  Only `isinstance(x, ndarray)` became `_is_array(x)` so that CUDA
+# tensors pass.  Everything above this block (device plumbing, slab pipeline, pinned pool) is original.
+# ---------------------------------------------------------------------------------------------------------
+
+
 def _normalize_inputs(X):
     if _is_array(X):
         Xs = [X]
