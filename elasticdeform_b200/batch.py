@@ -37,24 +37,44 @@ def deform_grid_batch(Xs, displacements, order=3, mode='constant', cval=0.0, cro
     assert len(displacements) == nb, 'one displacement per volume'
     if affines is not None:
         assert len(affines) == nb, 'one affine per volume'
+    if nb == 0:
+        return []
     device = _dg._device_of(Xs)
     problems = (_lib.EdfProblem * nb)()
     keep, outs, dxs = [], [], []
+    # everything that does not depend on the volume is normalised once when the batch is uniform (same shape and
+    # dtype throughout: the data-augmentation case); the per-volume Python work is then the inverse affine (when the
+    # affines differ) and one edf_problem
+    uniform = all(tuple(x.shape) == tuple(Xs[0].shape) and x.dtype == Xs[0].dtype for x in Xs)
+    shared = None
     with torch.cuda.device(device):
+        d_all = _prefilter_displacements_stacked(lib, displacements, Xs[0], device)
+        inv_cache = {}
         for b in range(nb):
             X = [Xs[b]]
-            if gradient:
-                shp = tuple(X_shape) if X_shape is not None else tuple(Xs[b].shape)
-                meta = [_dg._ShapeOnly(shp)]
+            if shared is None or not uniform:
+                if gradient:
+                    shp = tuple(X_shape) if X_shape is not None else tuple(Xs[b].shape)
+                    meta = [_dg._ShapeOnly(shp)]
+                else:
+                    shp = None
+                    meta = X
+                axis, deform_shape = _dg._normalize_axis_list(None, meta)
+                out_shapes, offset = _dg._compute_output_shapes(meta, axis, deform_shape, crop)
+                od = _dg._normalize_order(order, X)
+                md = _dg._normalize_mode(mode, X)
+                cv = _dg._normalize_cval(cval, X)
+                shared = (shp, axis, out_shapes, offset, od, md, cv)
+            shp, axis, out_shapes, offset, od, md, cv = shared
+            aff = None if affines is None else affines[b]
+            key = id(aff)
+            if key not in inv_cache:
+                inv_cache[key] = _dg._compute_inverse_affine(_dg._normalize_affine(aff, axis))
+            inv = inv_cache[key]
+            if d_all is not None:
+                d_f = d_all[b]
             else:
-                meta = X
-            axis, deform_shape = _dg._normalize_axis_list(None, meta)
-            out_shapes, offset = _dg._compute_output_shapes(meta, axis, deform_shape, crop)
-            od = _dg._normalize_order(order, X)
-            md = _dg._normalize_mode(mode, X)
-            cv = _dg._normalize_cval(cval, X)
-            inv = _dg._compute_inverse_affine(_dg._normalize_affine(None if affines is None else affines[b], axis))
-            d_f = _dg._prefilter_displacement(lib, _dg._normalize_displacement(displacements[b], X, axis), device)
+                d_f = _dg._prefilter_displacement(lib, _dg._normalize_displacement(displacements[b], X, axis), device)
             xd = _dg._to_device(Xs[b], device)
             if gradient:
                 if tuple(out_shapes[0]) != tuple(xd.shape):
@@ -88,6 +108,38 @@ def deform_grid_batch(Xs, displacements, order=3, mode='constant', cval=0.0, cro
                 res.append(_dg._from_device(dx, Xs[b]))
             return res
         return [_dg._from_device(o, x) for o, x in zip(outs, Xs)]
+
+
+def _prefilter_displacements_stacked(lib, displacements, X0, device):
+    """The control grids of the whole batch, prefiltered in naxis launches: grids of one shape and dtype are stacked
+    into one (batch, naxis, P...) array and filtered along the grid axes together (the per-line arithmetic is the
+    same as for one grid, so the result is bit-identical to ``_prefilter_displacement`` per volume).  Returns a
+    tensor indexable by volume, or None when the grids cannot be stacked."""
+    torch = _dg.torch
+    nb = len(displacements)
+    d0 = displacements[0]
+    if _dg._is_tensor(d0):
+        if not all(_dg._is_tensor(d) and d.shape == d0.shape and d.dtype == d0.dtype and d.device == d0.device
+                   for d in displacements):
+            return None
+        if d0.ndim != X0.ndim + 1 or d0.shape[0] != X0.ndim:
+            return None
+        stacked = torch.stack([d.detach() for d in displacements]).to(device)
+    else:
+        arrs = [numpy.asarray(d) for d in displacements]
+        if not all(a.shape == arrs[0].shape and a.dtype == arrs[0].dtype for a in arrs):
+            return None
+        if arrs[0].ndim != X0.ndim + 1 or arrs[0].shape[0] != X0.ndim:
+            return None
+        stacked = torch.from_numpy(numpy.stack(arrs)).to(device)
+    if stacked.dtype not in (torch.float64, torch.float32):
+        return None
+    out = torch.empty_like(stacked)
+    src = stacked
+    for ax in range(2, stacked.ndim):
+        _dg._spline_filter1d_device(lib, src, out, ax, 3)
+        src = out
+    return out
 
 
 def deform_random_grid_batch(Xs, sigma=25, points=3, order=3, mode='constant', cval=0.0, crop=None,

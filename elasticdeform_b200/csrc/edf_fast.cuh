@@ -699,6 +699,22 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
     bool done[EDF_MAX_INPUTS] = {false};
     for (int ii = 0; ii < p.ninputs; ++ii) {
         if (done[ii] || cls[ii] == EDF_CLASS_NONE) continue;
+        // orders 0 / 1 forward, 'constant' mode, 4-byte elements -- float32 volumes with or without a channel axis, and
+        // 4-byte label volumes at order 0 (bit copy): the polynomial-coordinate direct kernel, channel loop inside
+        if (!p.gradient && (cls[ii] == EDF_CLASS_F32 || cls[ii] == EDF_CLASS_COPY) && p.inp[ii].order <= 1 &&
+            !(flags & (EDF_FLAG_STAGED_FWD | EDF_FLAG_NO_WINDOW)) &&
+            (p.inp[ii].nstep_rank == 1 || cls[ii] == EDF_CLASS_COPY) && edf_poly_direct_eligible(p, L, ii)) {
+            L.input_mask = 1u << ii;
+            if (edf_poly_direct_launch(p.inp[ii].order, st, p, L, ii) == 0) {
+                g_fast_launch_error = cudaGetLastError();
+                if (g_fast_launch_error != cudaSuccess) return -1;
+                *name = "poly3d_f32_direct";
+                done[ii] = true;
+                ++launches;
+                *handled_mask |= 1u << ii;
+                continue;
+            }
+        }
         if (cls[ii] == EDF_CLASS_F32 && edf_lean_eligible(p, L, ii)) {
             L.input_mask = 1u << ii;
             // small volumes: fewer rows per CTA until the grid fills the 148 SMs at least twice over
@@ -741,7 +757,7 @@ static int edf_fast_try_launch(const EdfParams& p, cudaStream_t st, const char**
                 const bool big = (uint64_t)p.odim[0] * (uint64_t)p.odim[1] * (uint64_t)p.odim[2] >= EDF_SWIN_FWD_MIN_VOXELS;
                 const bool want = (flags & EDF_FLAG_STAGED_FWD) || edf_swin_fwd_env() ||
                                   (!steep && big && ord >= 2 && ord <= edf_swin_max_fwd_order());
-                if (want && edf_tile_env() && edf_tile_fwd_eligible(p, L, ii)) {
+                if (want && (edf_tile_env() || (flags & EDF_FLAG_STAGED_FWD)) && edf_tile_fwd_eligible(p, L, ii)) {
                     rcs = edf_tile_launch_fwd(ord, st, p, L, ii);
                     tile = rcs == 0;
                 }

@@ -18,12 +18,11 @@
 // coefficients are all zero gets a == 0 exactly (identity transform: no re-evaluation needed).
 #pragma once
 #include "edf_swin.cuh"
+#include "edf_fx.cuh"     // polynomial build, fold and fixed-point coordinates
 
-#define EDF_PL_TX 32               // x positions per warp / CTA
 #define EDF_PL_G 8                 // z-slabs per CTA (one warp each)
 #define EDF_PL_THREADS (EDF_PL_TX * EDF_PL_G)
 #define EDF_PL_RY 64               // rows a CTA walks through (table capacity)
-#define EDF_PL_NC 8                // control columns the 32 lanes of a warp can touch (span + 4)
 #define EDF_PL_MAXWARPS 16         // warps per CTA of the largest kernel using these tables
 
 struct EdfPolyTables {
@@ -60,70 +59,6 @@ __device__ __forceinline__ void edf_poly_tables(const EdfParams& p, EdfPolyTable
     __syncthreads();
 }
 
-// Rebuild the polynomial coefficients of this thread's column for the control interval whose window starts at
-// control row j0.  Warp-collective (all 32 lanes).  Returns the warp's gate: false when every control
-// coefficient the warp touches is zero (then a == 0 exactly).
-template <class Tab>
-__device__ __forceinline__ bool edf_poly_build(const EdfParams& p, Tab& s, int g, int lane, int j0, double* a /*[3][4]*/, int tw = -1)
-{
-    static_assert(EDF_PL_NC == 8, "lane -> (control row, control column) mapping");
-    if (tw < 0) tw = g;                                            // table slot of this warp
-    const int j = lane >> 3, kx = lane & 7;
-    const int sx0 = s.sx[0];
-    const int nxw = s.sx[EDF_PL_TX - 1] - sx0 + 4;
-    bool nz = false;
-    __syncwarp();
-    if (kx < nxw) {
-        const int my = edf_mirror_index32(j0 + j, (int)p.ncp[1]);
-        const int mx = edf_mirror_index32(sx0 + kx, (int)p.ncp[2]);
-        const bool f64 = p.ddtype == EDF_F64;
-        int64_t oz[4];
-        double w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            oz[i] = (int64_t)edf_mirror_index32(s.sz[g] + i, (int)p.ncp[0]) * p.dstr[1];
-            w[i] = s.wz[g][i];
-        }
-        const char* base = p.disp + (int64_t)my * p.dstr[2] + (int64_t)mx * p.dstr[3];
-#pragma unroll
-        for (int h = 0; h < 3; ++h) {
-            const char* bh = base + p.dstr[0] * h;
-            double acc = 0.0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double cf = f64 ? *(const double*)(bh + oz[i]) : (double)*(const float*)(bh + oz[i]);
-                nz |= (cf != 0.0);
-                acc = fma(cf, w[i], acc);
-            }
-            s.T[tw][h][j][kx] = acc;
-        }
-    }
-    const bool gate = __any_sync(0xffffffffu, nz);
-    // (the __any_sync above orders the table writes before the reads below)
-    const int sxrel = s.sx[lane] - sx0;
-    double wx[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) wx[k] = s.wx[lane][k];
-#pragma unroll
-    for (int h = 0; h < 3; ++h) {
-        double E[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            double e = 0.0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) e = fma(s.T[tw][h][jj][sxrel + k], wx[k], e);
-            E[jj] = e;
-        }
-        // uniform cubic B-spline segment -> power basis in u (weights as in deform.c:171-177)
-        a[h * 4 + 0] = (E[0] + 4.0 * E[1] + E[2]) * (1.0 / 6.0);
-        a[h * 4 + 1] = (E[2] - E[0]) * 0.5;
-        a[h * 4 + 2] = (E[0] - 2.0 * E[1] + E[2]) * 0.5;
-        a[h * 4 + 3] = ((E[3] - E[0]) + 3.0 * (E[1] - E[2])) * (1.0 / 6.0);
-    }
-    __syncwarp();
-    return gate;
-}
-
 // out-of-line form for kernels that check the interval row by row (several call sites): the coefficients come
 // back through a local array that the caller copies into its registers
 __device__ __noinline__ bool edf_poly_build_nl(const EdfParams& p, EdfPolyTables& s, int g, int lane, int j0, double* out)
@@ -139,100 +74,6 @@ __device__ __forceinline__ void edf_poly_eval(const double* a, double u, double&
     dx = fma(fma(fma(a[11], u, a[10]), u, a[9]), u, a[8]);
 }
 
-
-// ---------------------------------------------------------------------------------------------------------
-// Fixed-point source coordinates.  The row's own index, the crop offset and the affine map (deform.c:771-781)
-// are folded into the column's polynomial, and so is the constant 1.5 * 2^29: the last FMA of the Horner form
-// then rounds the SOURCE COORDINATE c to a multiple of 2^-23, and floor / fractional offset / range tests are
-// integer operations on the two words of the result -- no conversion instructions, no fp64 compares:
-//     T = c + 1.5*2^29   ->   floor(c) = bits [23,55) of T - const,    frac(c) = (lo & 0x7fffff) * 2^-23.
-// Even orders fold another 0.5 in (their window start is floor(c + 0.5), deform.c:784-788).  The quantisation
-// moves a coordinate by < 1.2e-7; voxels within 2^-21 of a threshold (integer coordinates for odd orders, integer
-// and half-integer ones for even orders) are flagged `slow` and redone in the reference order, so every discrete
-// decision still equals the reference's.
-// ---------------------------------------------------------------------------------------------------------
-#define EDF_PP_FBITS 23
-#define EDF_PP_MAGIC 805306368.0   // 1.5 * 2^29: ulp 2^-23
-#define EDF_PP_HI0 0x41C00000u     // high word of 2^29 (exponent 1052)
-#define EDF_PP_FLBIAS 0x90000000u  // bits [23,55) of the pattern of EDF_PP_MAGIC
-#define EDF_PP_NEAR 4.7683716e-7f  // 2^-21: four steps of the 2^-23 grid (quantisation: half a step each for the fold and the last FMA)
-
-// a[h*4 + k] (displacement along axis h as a cubic in u, edf_poly_build) -> out[h*4 + k]: source coordinate
-// (+ 0.5 for even orders) + 1.5*2^29 of the column (z, x) as a cubic in u, for the control interval whose window
-// starts at control row j0.  r = (I_y - 1) / (P_y - 1): y + off_y = (j0 + 1 + u) * r  (cp = (P-1)(y+off)/(I-1), deform.c:655)
-template <int ORDER>
-__device__ __forceinline__ void edf_poly_fold(const EdfParams& p, const double* a, double r, int j0, int z, int x, double* out)
-{
-    const double yj = xmul((double)(j0 + 1), r);
-    const double half = (ORDER & 1) ? 0.0 : 0.5;
-    if (p.has_affine) {
-        const double yo = xsub(yj, p.ooff_d[1]);                 // output row index at u = 0
-#pragma unroll
-        for (int h = 0; h < 3; ++h) {
-            const double* A = p.affine + h * 4;
-            const double c = fma(A[0], (double)z, fma(A[1], yo, fma(A[2], (double)x, A[3]))) + p.ooff_d[h];
-            out[h * 4 + 0] = ((a[h * 4 + 0] + c) + half) + EDF_PP_MAGIC;
-            out[h * 4 + 1] = fma(A[1], r, a[h * 4 + 1]);
-            out[h * 4 + 2] = a[h * 4 + 2];
-            out[h * 4 + 3] = a[h * 4 + 3];
-        }
-    } else {
-#pragma unroll
-        for (int h = 0; h < 3; ++h) {
-            const double c = (h == 0) ? xadd((double)z, p.ooff_d[0]) : (h == 1) ? yj : xadd((double)x, p.ooff_d[2]);
-            out[h * 4 + 0] = ((a[h * 4 + 0] + c) + half) + EDF_PP_MAGIC;
-            out[h * 4 + 1] = (h == 1) ? a[h * 4 + 1] + r : a[h * 4 + 1];
-            out[h * 4 + 2] = a[h * 4 + 2];
-            out[h * 4 + 3] = a[h * 4 + 3];
-        }
-    }
-}
-
-// Source coordinates of one voxel from the folded polynomial (see the header): window starts, centred fractional
-// offsets e = frac - 0.5, strict in-range flag and `slow` (redo in the reference order).
-struct EdfPipeVoxel {
-    int stz, sty, stx;
-    float ez, ey, ex;
-    bool inr, slow;
-};
-template <int ORDER>
-__device__ __forceinline__ void edf_pipe_coords(const double* a, double u, bool gate, int lenz, int leny, int lenx,
-                                                unsigned rngz, unsigned rngy, unsigned rngx, EdfPipeVoxel& v)
-{
-    const double Tz = fma(fma(fma(a[3], u, a[2]), u, a[1]), u, a[0]);
-    const double Ty = fma(fma(fma(a[7], u, a[6]), u, a[5]), u, a[4]);
-    const double Tx = fma(fma(fma(a[11], u, a[10]), u, a[9]), u, a[8]);
-    const unsigned loz = (unsigned)__double2loint(Tz), hiz = (unsigned)__double2hiint(Tz);
-    const unsigned loy = (unsigned)__double2loint(Ty), hiy = (unsigned)__double2hiint(Ty);
-    const unsigned lox = (unsigned)__double2loint(Tx), hix = (unsigned)__double2hiint(Tx);
-    // |c| < 2^28 (and not NaN): the exponent field of all three results is that of 2^29
-    const bool expok = (((hiz - EDF_PP_HI0) | (hiy - EDF_PP_HI0) | (hix - EDF_PP_HI0)) < 0x00100000u);
-    const int flz = (int)(__funnelshift_r(loz, hiz, EDF_PP_FBITS) - EDF_PP_FLBIAS);
-    const int fly = (int)(__funnelshift_r(loy, hiy, EDF_PP_FBITS) - EDF_PP_FLBIAS);
-    const int flx = (int)(__funnelshift_r(lox, hix, EDF_PP_FBITS) - EDF_PP_FLBIAS);
-    const unsigned gqz = loz & 0x7fffffu, gqy = loy & 0x7fffffu, gqx = lox & 0x7fffffu;
-    v.ez = __uint_as_float(gqz | 0x3f800000u) - 1.5f;             // exact
-    v.ey = __uint_as_float(gqy | 0x3f800000u) - 1.5f;
-    v.ex = __uint_as_float(gqx | 0x3f800000u) - 1.5f;
-    bool near;
-    if (ORDER & 1) {
-        v.inr = ((unsigned)flz <= rngz) & ((unsigned)fly <= rngy) & ((unsigned)flx <= rngx);
-        near = !(fmaxf(fmaxf(fabsf(v.ez), fabsf(v.ey)), fabsf(v.ex)) < 0.5f - EDF_PP_NEAR);
-    } else {
-        // T holds c + 0.5: floor(2c + 1) = 2 * floor + (frac >= 0.5); c in [0, len-1] <=> 1 <= that <= 2 len - 1
-        const unsigned hz = 2u * (unsigned)flz + (gqz >> 22), hy = 2u * (unsigned)fly + (gqy >> 22), hx = 2u * (unsigned)flx + (gqx >> 22);
-        v.inr = (hz - 1u <= rngz) & (hy - 1u <= rngy) & (hx - 1u <= rngx);
-        const float qz = fabsf(fabsf(v.ez) - 0.25f), qy = fabsf(fabsf(v.ey) - 0.25f), qx = fabsf(fabsf(v.ex) - 0.25f);
-        near = !(fmaxf(fmaxf(qz, qy), qx) < 0.25f - EDF_PP_NEAR);
-    }
-    v.slow = (gate & near) | !expok;
-    if (!v.inr & !v.slow) {
-        // exactly on the upper limit (un-gated integer coordinates: identity maps): in range in the reference
-        const unsigned k = (ORDER & 1) ? 0u : 0x400000u;
-        v.slow = ((flz == lenz - 1) & (gqz == k)) | ((fly == leny - 1) & (gqy == k)) | ((flx == lenx - 1) & (gqx == k));
-    }
-    v.stz = flz - ORDER / 2; v.sty = fly - ORDER / 2; v.stx = flx - ORDER / 2;
-}
 
 // Lean form for the direct kernels: the same fixed-point coordinates with the flags folded into one code,
 //     >= 0 : element offset of the first tap (in range, taps inside the volume -- orders 0 / 1, 'constant' mode)
@@ -351,6 +192,9 @@ edf_poly3d_fwd_direct_kernel(const __grid_constant__ EdfParams p, const __grid_c
     const float cvalf = __uint_as_float((uint32_t)L.cval_bits[ii]);
     const int nrow = min(ry, ody - y0);
     const double rrat = s.rrat;
+    // non-deformed "step" axis (channels sharing the displacement): element strides, 1 step when there is none
+    const int64_t nsteps = d.nstep_rank == 1 ? d.nsteps : 1;
+    const int64_t in_step = d.nstep_rank == 1 ? d.in_step_str[0] / 4 : 0, out_step = d.nstep_rank == 1 ? d.out_step_str[0] / 4 : 0;
     const unsigned hlf = (ORDER & 1) ? 0u : 0x400000u;
     const unsigned limloz = ((unsigned)(lenz - 1) << EDF_PP_FBITS) + hlf, limloy = ((unsigned)(leny - 1) << EDF_PP_FBITS) + hlf,
                    limlox = ((unsigned)(lenx - 1) << EDF_PP_FBITS) + hlf;
@@ -383,41 +227,48 @@ edf_poly3d_fwd_direct_kernel(const __grid_constant__ EdfParams p, const __grid_c
             e[u] = edf_fx_code<ORDER>(a, s.u[m], gate, rngz, rngy, rngx, limloz, limloy, limlox, isz, isy, fz[u], fy[u], fx[u]);
             emin = min(emin, e[u]);
         }
-        float t[U];
-        if (ORDER == 0) {
+        // taps and stores, once per non-deformed step (channel): the coordinates above are shared by all of them
+        // (deform.c:828-838 loops the steps inside the voxel loop as well)
+        const float* pin_c = pin;
+        float* pout_c = pout;
+#pragma unroll 1
+        for (int64_t ss = 0; ss < nsteps; ++ss, pin_c += in_step, pout_c += out_step) {
+            float t[U];
+            if (ORDER == 0) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) t[u] = __ldg(pin + max(e[u], 0));
-        } else {
-            float v[U][8];
+                for (int u = 0; u < U; ++u) t[u] = __ldg(pin_c + max(e[u], 0));
+            } else {
+                float v[U][8];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const float* b0 = pin + max(e[u], 0);
-                const float* b1 = b0 + isy;
-                const float* b2 = b0 + isz;
-                const float* b3 = b2 + isy;
-                v[u][0] = __ldg(b0); v[u][1] = __ldg(b0 + 1);
-                v[u][2] = __ldg(b1); v[u][3] = __ldg(b1 + 1);
-                v[u][4] = __ldg(b2); v[u][5] = __ldg(b2 + 1);
-                v[u][6] = __ldg(b3); v[u][7] = __ldg(b3 + 1);
+                for (int u = 0; u < U; ++u) {
+                    const float* b0 = pin_c + max(e[u], 0);
+                    const float* b1 = b0 + isy;
+                    const float* b2 = b0 + isz;
+                    const float* b3 = b2 + isy;
+                    v[u][0] = __ldg(b0); v[u][1] = __ldg(b0 + 1);
+                    v[u][2] = __ldg(b1); v[u][3] = __ldg(b1 + 1);
+                    v[u][4] = __ldg(b2); v[u][5] = __ldg(b2 + 1);
+                    v[u][6] = __ldg(b3); v[u][7] = __ldg(b3 + 1);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    // weights 0.5 -+ e from the centred offsets; x, then y, then z as in the other float32 kernels
+                    const float wx0 = 0.5f - fx[u], wx1 = 0.5f + fx[u];
+                    const float wy0 = 0.5f - fy[u], wy1 = 0.5f + fy[u];
+                    const float wz0 = 0.5f - fz[u], wz1 = 0.5f + fz[u];
+                    const float r00 = fmaf(v[u][1], wx1, v[u][0] * wx0);
+                    const float r01 = fmaf(v[u][3], wx1, v[u][2] * wx0);
+                    const float r10 = fmaf(v[u][5], wx1, v[u][4] * wx0);
+                    const float r11 = fmaf(v[u][7], wx1, v[u][6] * wx0);
+                    const float p0 = fmaf(r01, wy1, r00 * wy0);
+                    const float p1 = fmaf(r11, wy1, r10 * wy0);
+                    t[u] = fmaf(p1, wz1, p0 * wz0);
+                }
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                // weights 0.5 -+ e from the centred offsets; x, then y, then z as in the other float32 kernels
-                const float wx0 = 0.5f - fx[u], wx1 = 0.5f + fx[u];
-                const float wy0 = 0.5f - fy[u], wy1 = 0.5f + fy[u];
-                const float wz0 = 0.5f - fz[u], wz1 = 0.5f + fz[u];
-                const float r00 = fmaf(v[u][1], wx1, v[u][0] * wx0);
-                const float r01 = fmaf(v[u][3], wx1, v[u][2] * wx0);
-                const float r10 = fmaf(v[u][5], wx1, v[u][4] * wx0);
-                const float r11 = fmaf(v[u][7], wx1, v[u][6] * wx0);
-                const float p0 = fmaf(r01, wy1, r00 * wy0);
-                const float p1 = fmaf(r11, wy1, r10 * wy0);
-                t[u] = fmaf(p1, wz1, p0 * wz0);
-            }
+            for (int u = 0; u < U; ++u)
+                if (tok & (u < nb) & (e[u] != -2)) pout_c[obase_zx + (y0 + m0 + u) * osy] = e[u] >= 0 ? t[u] : cvalf;
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (tok & (u < nb) & (e[u] != -2)) pout[obase_zx + (y0 + m0 + u) * osy] = e[u] >= 0 ? t[u] : cvalf;
         if ((emin == -2) & tok) {
 #pragma unroll 1
             for (int u = 0; u < U; ++u)
@@ -429,8 +280,17 @@ edf_poly3d_fwd_direct_kernel(const __grid_constant__ EdfParams p, const __grid_c
 // order 0/1 direct kernel: conditions on top of edf_lean_eligible
 static bool edf_poly_direct_eligible(const EdfParams& p, const EdfFastLaunch& L, int ii)
 {
-    if (!edf_lean_eligible(p, L, ii)) return false;
+    // 3-D, 4-byte elements (float32 at orders 0 / 1; any 4-byte type at order 0: the output is a bit copy), unit
+    // stride along x, at most one non-deformed step axis (channels), 'constant' mode
+    if (p.naxis != 3) return false;
     const EdfInputDesc& d = p.inp[ii];
+    if (d.in_dtype != d.out_dtype || edf_elem_size(d.in_dtype) != 4) return false;
+    if (d.in_dtype != EDF_F32 && d.order != 0) return false;
+    if (d.nstep_rank > 1) return false;
+    if (d.nstep_rank == 1 && ((d.in_step_str[0] % 4) || (d.out_step_str[0] % 4))) return false;
+    if (L.istr_e[ii][2] != 1) return false;
+    for (int a = 0; a < 3; ++a)
+        if (p.idim[a] < 8) return false;
     if (d.mode != EDF_MODE_CONSTANT || d.order > 1) return false;
     if (p.ncp[1] < 2) return false;                                // the row index is folded into the polynomial in u
     for (int a = 0; a < 3; ++a)

@@ -748,7 +748,7 @@ edf_swin3d_grad_kernel(const __grid_constant__ EdfParams p, const __grid_constan
                 }
             }
 #pragma unroll
-            for (int u = 0; u < EDF_SW_MR; ++u) {
+            for (int u = 0; u < EDF_SW_MR; u += 2) {              // rows 0 and 2 of the chunk: a magnifying map shows in every row
                 const unsigned mine = ((actm >> u) & 1u) ? pk[u] : 0u;
                 const unsigned next = __shfl_down_sync(0xffffffffu, mine, 1);
                 unsigned m = __ballot_sync(0xffffffffu, (lane < 31) & (mine != 0u) & (next + 1u == mine));

@@ -137,3 +137,42 @@ def test_fixedpoint_headline_slab(edf):
         ref = O.deform_grid(X, D, order=3, prefilter=False, crop=crop, impl=_impl())
         np.testing.assert_allclose(part, ref, rtol=0, atol=1e-5)
         np.testing.assert_allclose(full[crop], ref, rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.uint32])
+def test_fixedpoint_label_volume_bit_copy(edf, dtype):
+    """4-byte label volumes at order 0 take the same direct kernel (the output is a bit copy of the selected voxel,
+    or the converted cval): BASELINE config 3's int32 label."""
+    from elasticdeform_b200 import _lib
+    rng = np.random.default_rng(6000)
+    L = rng.integers(0, 2 ** 31 - 1, (40, 56, 72)).astype(dtype)
+    D = rng.standard_normal((3, 4, 4, 4)) * 5.0
+    for kw in (dict(), dict(cval=7), dict(crop=(slice(3, 30), slice(None), slice(10, 60)))):
+        y = edf.deform_grid(L, D, order=0, prefilter=False, **kw)
+        assert _lib.last_kernel() == "poly3d_f32_direct", _lib.last_kernel()
+        yr = O.deform_grid(L, D, order=0, prefilter=False, impl=_impl(), **kw)
+        assert y.dtype == yr.dtype
+        np.testing.assert_array_equal(y, yr)
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_fixedpoint_channels_share_coordinates(edf, order):
+    """One array of channels sharing a displacement (axis=(1, 2, 3), BASELINE config 5): one coordinate pass per
+    voxel, the channel loop inside the kernel."""
+    from elasticdeform_b200 import _lib
+    rng = np.random.default_rng(6100 + order)
+    X = rng.random((5, 40, 48, 72), dtype=np.float32)
+    D = rng.standard_normal((3, 5, 5, 5)) * 4.0
+    for kw in (dict(), dict(crop=(slice(4, 36), slice(8, 40), slice(0, 64)))):
+        y = edf.deform_grid(X, D, order=order, axis=(1, 2, 3), prefilter=False, **kw)
+        assert _lib.last_kernel() == "poly3d_f32_direct", _lib.last_kernel()
+        yr = O.deform_grid(X, D, order=order, axis=(1, 2, 3), prefilter=False, impl=_impl(), **kw)
+        if order == 0:
+            np.testing.assert_array_equal(y, yr)
+        else:
+            np.testing.assert_allclose(y, yr, rtol=0, atol=1e-5)
+    # a strided view (every other channel): the step stride is not the dense one
+    Xv = X[::2]
+    y = edf.deform_grid(Xv, D, order=order, axis=(1, 2, 3), prefilter=False)
+    yr = O.deform_grid(np.ascontiguousarray(Xv), D, order=order, axis=(1, 2, 3), prefilter=False, impl=_impl())
+    np.testing.assert_allclose(y, yr, rtol=0, atol=1e-5)
