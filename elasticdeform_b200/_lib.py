@@ -70,7 +70,7 @@ class EdfProblem(ctypes.Structure):
 
 # every symbol include/edf_b200.h declares (checked by tests/test_host_api.py)
 EXPORTED_SYMBOLS = (
-    "edf_deform_grid", "edf_deform_grid_grad", "edf_deform_grid_batch",
+    "edf_deform_grid", "edf_deform_grid_grad", "edf_deform_grid_batch", "edf_deform_grid_batch_uniform",
     "edf_spline_filter1d", "edf_spline_filter1d_grad", "edf_last_error",
     "edf_version", "edf_device_ok", "edf_launch_count", "edf_last_kernel", "edf_debug_tile_profile",
 )
@@ -105,6 +105,10 @@ def load_library():
         lib.edf_deform_grid_grad.restype = ctypes.c_int
         lib.edf_deform_grid_batch.argtypes = [ctypes.POINTER(EdfProblem), i32, i32, vp]
         lib.edf_deform_grid_batch.restype = ctypes.c_int
+        u64p = ctypes.POINTER(ctypes.c_uint64)
+        lib.edf_deform_grid_batch_uniform.argtypes = [ctypes.POINTER(EdfProblem), i32, i32, u64p, u64p, u64p,
+                                                      ctypes.POINTER(ctypes.c_double), vp]
+        lib.edf_deform_grid_batch_uniform.restype = ctypes.c_int
         lib.edf_spline_filter1d.argtypes = [ctypes.POINTER(EdfArray), ctypes.POINTER(EdfArray), i32, i32, vp]
         lib.edf_spline_filter1d.restype = ctypes.c_int
         lib.edf_spline_filter1d_grad.argtypes = [ctypes.POINTER(EdfArray), ctypes.POINTER(EdfArray), i32, i32, vp]

@@ -49,6 +49,10 @@ def deform_grid_batch(Xs, displacements, order=3, mode='constant', cval=0.0, cro
     shared = None
     with torch.cuda.device(device):
         d_all = _prefilter_displacements_stacked(lib, displacements, Xs[0], device)
+        if uniform and d_all is not None and not (prefilter and int(_dg._normalize_order(order, [0])[0]) > 1):
+            res = _uniform_batch(lib, device, Xs, d_all, order, mode, cval, crop, affines, gradient, X_shape, _flags)
+            if res is not None:
+                return res
         inv_cache = {}
         for b in range(nb):
             X = [Xs[b]]
@@ -108,6 +112,63 @@ def deform_grid_batch(Xs, displacements, order=3, mode='constant', cval=0.0, cro
                 res.append(_dg._from_device(dx, Xs[b]))
             return res
         return [_dg._from_device(o, x) for o, x in zip(outs, Xs)]
+
+
+def _uniform_batch(lib, device, Xs, d_all, order, mode, cval, crop, affines, gradient, X_shape, flags):
+    """Volumes of one shape and dtype without a per-volume prefilter: ONE edf_problem describes the batch and the
+    C-ABI receives three arrays of device addresses (edf_deform_grid_batch_uniform); the per-volume Python work is
+    reading a data pointer.  Returns None when the batch does not qualify (strided views with different layouts)."""
+    torch = _dg.torch
+    nb = len(Xs)
+    X0 = [Xs[0]]
+    if gradient:
+        shp = tuple(X_shape) if X_shape is not None else tuple(Xs[0].shape)
+        meta = [_dg._ShapeOnly(shp)]
+    else:
+        shp = None
+        meta = X0
+    axis, deform_shape = _dg._normalize_axis_list(None, meta)
+    out_shapes, offset = _dg._compute_output_shapes(meta, axis, deform_shape, crop)
+    od = _dg._normalize_order(order, X0)
+    md = _dg._normalize_mode(mode, X0)
+    cv = _dg._normalize_cval(cval, X0)
+    naxis = len(axis[0])
+    # inverse affine maps of the whole batch in one vectorised inversion
+    inv_all = None
+    if affines is not None:
+        A = numpy.stack([_dg._normalize_affine(a, axis) for a in affines])          # (nb, n, n + 1)
+        Ainv = numpy.linalg.inv(A[:, :, :naxis])
+        inv_all = numpy.concatenate([Ainv, -numpy.einsum('bij,bj->bi', Ainv, A[:, :, naxis])[:, :, None]], axis=2)
+        inv_all = numpy.ascontiguousarray(inv_all, dtype='float64')
+    xs = [_dg._to_device(x, device) for x in Xs]
+    if not all(x.stride() == xs[0].stride() for x in xs):
+        return None
+    if gradient:
+        if tuple(out_shapes[0]) != tuple(xs[0].shape):
+            raise ValueError("X_shape does not match output shape and cropping.")
+        acc = torch.zeros((nb,) + tuple(shp), dtype=xs[0].dtype, device=device)
+        ins0, outs0 = acc[0], xs[0]
+        in_ptrs = acc.data_ptr() + numpy.arange(nb, dtype=numpy.uint64) * numpy.uint64(acc.stride(0) * acc.element_size())
+        out_ptrs = numpy.array([x.data_ptr() for x in xs], dtype=numpy.uint64)
+        results = acc
+    else:
+        res_all = torch.empty((nb,) + tuple(out_shapes[0]), dtype=xs[0].dtype, device=device)
+        ins0, outs0 = xs[0], res_all[0]
+        in_ptrs = numpy.array([x.data_ptr() for x in xs], dtype=numpy.uint64)
+        out_ptrs = res_all.data_ptr() + numpy.arange(nb, dtype=numpy.uint64) * numpy.uint64(res_all.stride(0) * res_all.element_size())
+        results = res_all
+    disp_ptrs = d_all.data_ptr() + numpy.arange(nb, dtype=numpy.uint64) * numpy.uint64(d_all.stride(0) * d_all.element_size())
+    proto, keep = _dg._build_problem([ins0], [outs0], d_all[0], offset, axis, od, md, cv,
+                                     None if inv_all is None else inv_all[0], flags)
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    in_ptrs = numpy.ascontiguousarray(in_ptrs, dtype=numpy.uint64)
+    out_ptrs = numpy.ascontiguousarray(out_ptrs, dtype=numpy.uint64)
+    disp_ptrs = numpy.ascontiguousarray(disp_ptrs, dtype=numpy.uint64)
+    aff_p = None if inv_all is None else inv_all.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    _lib.check(lib.edf_deform_grid_batch_uniform(ctypes.byref(proto), nb, 1 if gradient else 0,
+                                                 in_ptrs.ctypes.data_as(u64p), out_ptrs.ctypes.data_as(u64p),
+                                                 disp_ptrs.ctypes.data_as(u64p), aff_p, _dg._stream_ptr(device)))
+    return [_dg._from_device(results[b], Xs[b]) for b in range(nb)]
 
 
 def _prefilter_displacements_stacked(lib, displacements, X0, device):

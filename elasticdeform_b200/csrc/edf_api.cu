@@ -48,12 +48,14 @@ extern "C" int edf_device_ok(void)
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
-    int major = 0;
-    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    // the library holds sm_100a SASS only (no PTX): exactly compute capability 10.0
+    int major = 0, minor = -1;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
-    return major >= 10 ? 1 : 0;
+    return (major == 10 && minor == 0) ? 1 : 0;
 }
 
 static int check_launch(const char* what)
@@ -143,24 +145,46 @@ extern "C" int edf_deform_grid_grad(const edf_problem* problem, void* stream)
 // caller's stream is preserved, nothing synchronises the host.
 #define EDF_BATCH_STREAMS 4
 struct EdfBatchStreams {
-    int device = -1;
+    bool ready = false;
     cudaStream_t s[EDF_BATCH_STREAMS] = {};
     cudaEvent_t fork = nullptr, join[EDF_BATCH_STREAMS] = {};
 };
-static thread_local EdfBatchStreams g_batch;
+// one set per device and thread, created on first use and kept (a thread that hops between devices finds its
+// earlier sets again); a set whose creation fails part-way is destroyed again
+#define EDF_BATCH_MAX_DEVICES 64
+static thread_local EdfBatchStreams g_batch_sets[EDF_BATCH_MAX_DEVICES];
+static thread_local EdfBatchStreams* g_batch_cur = nullptr;
+#define g_batch (*g_batch_cur)
+
+static void batch_streams_destroy(EdfBatchStreams& b)
+{
+    for (int i = 0; i < EDF_BATCH_STREAMS; ++i) {
+        if (b.s[i]) cudaStreamDestroy(b.s[i]);
+        if (b.join[i]) cudaEventDestroy(b.join[i]);
+        b.s[i] = nullptr;
+        b.join[i] = nullptr;
+    }
+    if (b.fork) cudaEventDestroy(b.fork);
+    b.fork = nullptr;
+    b.ready = false;
+    cudaGetLastError();
+}
 
 static int batch_streams_ready()
 {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (g_batch.device == dev) return 1;
-    // (re)create for this device; a thread that hops devices simply gets a new set
-    for (int i = 0; i < EDF_BATCH_STREAMS; ++i) {
-        if (cudaStreamCreateWithFlags(&g_batch.s[i], cudaStreamNonBlocking) != cudaSuccess) return 0;
-        if (cudaEventCreateWithFlags(&g_batch.join[i], cudaEventDisableTiming) != cudaSuccess) return 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= EDF_BATCH_MAX_DEVICES) return 0;
+    EdfBatchStreams& b = g_batch_sets[dev];
+    g_batch_cur = &b;
+    if (b.ready) return 1;
+    bool ok = true;
+    for (int i = 0; i < EDF_BATCH_STREAMS && ok; ++i) {
+        ok = cudaStreamCreateWithFlags(&b.s[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&b.join[i], cudaEventDisableTiming) == cudaSuccess;
     }
-    if (cudaEventCreateWithFlags(&g_batch.fork, cudaEventDisableTiming) != cudaSuccess) return 0;
-    g_batch.device = dev;
+    ok = ok && cudaEventCreateWithFlags(&b.fork, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { batch_streams_destroy(b); return 0; }
+    b.ready = true;
     return 1;
 }
 
@@ -189,6 +213,46 @@ extern "C" int edf_deform_grid_batch(const edf_problem* problems, int32_t n, int
     }
     if (rc == EDF_OK && cudaGetLastError() != cudaSuccess)
         return edf_fail(EDF_ERR_CUDA, "batch stream fork/join failed");
+    return rc;
+}
+
+extern "C" int edf_deform_grid_batch_uniform(const edf_problem* proto, int32_t n, int32_t gradient,
+                                             const uint64_t* in_ptrs, const uint64_t* out_ptrs, const uint64_t* disp_ptrs,
+                                             const double* affines, void* stream)
+{
+    if (n < 0 || !proto || (n > 0 && (!in_ptrs || !out_ptrs || !disp_ptrs))) return edf_fail(EDF_ERR_RUNTIME, "invalid batch");
+    if (proto->ninputs != 1 || !proto->inputs || !proto->outputs)
+        return edf_fail(EDF_ERR_RUNTIME, "uniform batch: one input per volume");
+    if (proto->naxis < 1 || proto->naxis > EDF_MAX_AXIS) return edf_fail(EDF_ERR_RUNTIME, "invalid number of axes");
+    cudaStream_t user = (cudaStream_t)stream;
+    const bool fork = n >= 2 && batch_streams_ready();
+    if (!fork) cudaGetLastError();
+    const int ns = fork ? (n < EDF_BATCH_STREAMS ? n : EDF_BATCH_STREAMS) : 1;
+    if (fork) {
+        cudaEventRecord(g_batch.fork, user);
+        for (int k = 0; k < ns; ++k) cudaStreamWaitEvent(g_batch.s[k], g_batch.fork, 0);
+    }
+    const int na = proto->naxis * (proto->naxis + 1);
+    int rc = EDF_OK;
+    for (int i = 0; i < n && rc == EDF_OK; ++i) {
+        edf_array in = proto->inputs[0], out = proto->outputs[0];
+        in.data = (void*)(uintptr_t)in_ptrs[i];
+        out.data = (void*)(uintptr_t)out_ptrs[i];
+        edf_problem pr = *proto;
+        pr.inputs = &in;
+        pr.outputs = &out;
+        pr.displacement.data = (void*)(uintptr_t)disp_ptrs[i];
+        if (affines) pr.affine = affines + (size_t)i * na;
+        rc = run_problem(&pr, gradient ? 1 : 0, fork ? g_batch.s[i % ns] : user);
+    }
+    if (fork) {
+        for (int k = 0; k < ns; ++k) {             // always join, also after an error
+            cudaEventRecord(g_batch.join[k], g_batch.s[k]);
+            cudaStreamWaitEvent(user, g_batch.join[k], 0);
+        }
+        if (rc == EDF_OK && cudaGetLastError() != cudaSuccess)
+            return edf_fail(EDF_ERR_CUDA, "batch stream fork/join failed");
+    }
     return rc;
 }
 

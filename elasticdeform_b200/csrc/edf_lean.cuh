@@ -649,6 +649,7 @@ struct EdfGradWinSmem {
     int    sx[EDF_GW_TX];
     int    ny, nx, nonzero, gmax_bits;
     int    wmin[3], pad_;
+    int    wmax[3], pad2_;          // density guard: extent of the chunk's corner coordinates
     unsigned rowmask[(EDF_GW_WZ * EDF_GW_WY + 31) / 32 + 1];   // window rows holding contributions (TMA flush)
     double A[3][EDF_GW_G][EDF_GW_NC][EDF_GW_NC];
     double Bw[EDF_GW_WARPS][3][EDF_GW_MR][EDF_GW_NC];
@@ -821,7 +822,7 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
                 while (jx >= nx) { jx -= nx; ++h; }
             }
         }
-        if (tid == 0) { s.wmin[0] = s.wmin[1] = s.wmin[2] = 0x7fffffff; s.gmax_bits = 0; }
+        if (tid == 0) { s.wmin[0] = s.wmin[1] = s.wmin[2] = 0x7fffffff; s.wmax[0] = s.wmax[1] = s.wmax[2] = (int)0x80000000; s.gmax_bits = 0; }
         __syncthreads();
         // ---- chunk statistics: max |dY| (fixed-point scale) and the window origin from the
         //      corner voxels of the chunk box
@@ -849,6 +850,9 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
                 atomicMin(&s.wmin[0], fz_);
                 atomicMin(&s.wmin[1], fy_);
                 atomicMin(&s.wmin[2], fx_);
+                atomicMax(&s.wmax[0], fz_);
+                atomicMax(&s.wmax[1], fy_);
+                atomicMax(&s.wmax[2], fx_);
             }
         }
         __syncthreads();
@@ -868,7 +872,12 @@ edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_cons
             const float scale = (ORDER >= 2) ? (4194304.0f * 0.999f) / (fmaxf(gmax_c, 1e-30f) * (WMAX * WMAX * WMAX))
                                              : ldexpf(1.0f, FIX - ex);
             const float inv_scale = (ORDER >= 2) ? 1.0f / scale : ldexpf(1.0f, ex - FIX);
-            const int wz0 = s.wmin[0] - (ORDER + 1) / 2 - EDF_GW_MARGIN;
+            // density guard (see edf_swin.cuh): where the map collapses -- the chunk's 1024 voxels land on a handful of
+            // cells -- the 32-bit fixed-point cells would wrap; such a chunk gets a window no voxel can hit and
+            // scatters straight to dX in float
+            const long long gcells = (long long)(s.wmax[0] - s.wmin[0] + 1) * (s.wmax[1] - s.wmin[1] + 1) * (s.wmax[2] - s.wmin[2] + 1);
+            const bool gdense = 1024 > 16 * gcells;
+            const int wz0 = gdense ? -0x20000000 : s.wmin[0] - (ORDER + 1) / 2 - EDF_GW_MARGIN;
             const int wy0 = s.wmin[1] - (ORDER + 1) / 2 - EDF_GW_MARGIN;
             const int wx0 = (s.wmin[2] - (ORDER + 1) / 2 - EDF_GW_MARGIN) & ~3;   // 16-byte aligned columns
             if (tok && ORDER <= 1) {

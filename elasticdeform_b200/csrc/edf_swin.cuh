@@ -45,7 +45,7 @@
 #define EDF_SW_MINBLOCKS 2         // resident CTAs per SM the register allocation aims at (3 needs EDF_SW_ROWS <= 208
 #endif                             //   and 85 registers per thread: see DESIGN.md (f) for what that costs in spills)
 #define EDF_SW_MAXQ (EDF_SW_PITCH / 4)
-#define EDF_SW_DENSE_MAX 96        // voxels of one chunk per window cell beyond which the gradient window is not used (see the density guard)
+#define EDF_SW_DENSE_MAX 16        // active voxels of a chunk per window start of its box beyond which the gradient window is not used
 #ifndef EDF_SWIN_GRAD_MAXORDER
 #define EDF_SWIN_GRAD_MAXORDER 3      // highest spline order the staged-window gradient kernel takes over by default
 #endif                                //   (measured on B200, 256^3: 0.24 / 0.27 / 0.47 / 0.77 ms at orders 0-3 against
@@ -350,7 +350,7 @@ edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
         s.nonzero = 0;
         if (EDF_SW_BULK) edf_mbar_init(&s.mbar, 1);
     }
-    if (tid < 3 * 8) (&s.bb[0][0])[tid] = ((tid & 7) < 3) ? INT_MAX : INT_MIN;
+    if (tid < 3 * 8) (&s.bb[0][0])[tid] = ((tid & 7) < 3) ? INT_MAX : ((tid & 7) == 7 ? 0 : INT_MIN);
     if (tid < EDF_SW_TX) {
         edf_fast_ctrl_entry(p, 2, min((int64_t)(x0 + tid), p.odim[2] - 1), s.wx[tid], &s.sx[tid]);
     } else if (tid < EDF_SW_TX + EDF_SW_RY) {
@@ -447,7 +447,7 @@ edf_swin3d_fwd_kernel(const __grid_constant__ EdfParams p, const __grid_constant
         __syncthreads();                                           // box complete; previous chunk's gathers done
         // the box of chunk c+2 (= chunk c-1's, no longer read) is reset here: chunk c+2's atomics come after
         // the next chunk's barrier
-        if (tid < 8) s.bb[par == 0 ? 2 : par - 1][tid] = (tid < 3) ? INT_MAX : INT_MIN;
+        if (tid < 8) s.bb[par == 0 ? 2 : par - 1][tid] = (tid < 3) ? INT_MAX : (tid == 7 ? 0 : INT_MIN);
         const int wz0 = s.bb[par][0], wy0 = s.bb[par][1], wx0 = s.bb[par][2] & ~3;
         const int nzw = s.bb[par][3] - wz0 + NT, nyw = s.bb[par][4] - wy0 + NT;
         const int nq = ((s.bb[par][5] + NT - 1 - wx0) >> 2) + 1;
@@ -631,7 +631,7 @@ edf_swin3d_grad_kernel(const __grid_constant__ EdfParams p, const __grid_constan
 
     // ---- prologue: control tables, z-contraction A, empty boxes, zero window
     if (tid == 0) s.nonzero = 0;
-    if (tid < 3 * 8) (&s.bb[0][0])[tid] = ((tid & 7) < 3) ? INT_MAX : INT_MIN;
+    if (tid < 3 * 8) (&s.bb[0][0])[tid] = ((tid & 7) < 3) ? INT_MAX : ((tid & 7) == 7 ? 0 : INT_MIN);
     if (tid < EDF_SW_TX) {
         edf_fast_ctrl_entry(p, 2, min((int64_t)(x0 + tid), p.odim[2] - 1), s.wx[tid], &s.sx[tid]);
     } else if (tid < EDF_SW_TX + EDF_SW_RY) {
@@ -731,42 +731,24 @@ edf_swin3d_grad_kernel(const __grid_constant__ EdfParams p, const __grid_constan
         mxx = __reduce_max_sync(0xffffffffu, mxx);
         const int gbits = __reduce_max_sync(0xffffffffu, __float_as_int(gmax));    // non-negative floats order as ints
         // Density guard: the 32-bit fixed-point cells hold ~128 (orders 0 / 1) to ~150 (orders >= 2) voxels' worth of
-        // mass.  Under strong local magnification (a 3-D affine zoom of ~5x or more) that many voxels of one chunk
-        // land on one cell and the accumulator would wrap.  Longest run of voxels with the SAME window start along x
-        // (neighbouring lanes) times the longest run along y (this thread's rows) times the 8 slabs bounds the
-        // multiplicity of a locally affine map; dense chunks scatter straight to dX in float instead.
-        int dens = 0;
-        if (mnz != INT_MAX || __any_sync(0xffffffffu, actm != 0u)) {
-            int yrun = 1, xrun = 1;
-            {
-                int run = 1;
-#pragma unroll
-                for (int u = 1; u < EDF_SW_MR; ++u) {
-                    const bool same = (((actm >> u) & (actm >> (u - 1))) & 1u) && (pk[u] + 1024u == pk[u - 1]);
-                    run = same ? run + 1 : 1;
-                    yrun = max(yrun, run);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < EDF_SW_MR; u += 2) {              // rows 0 and 2 of the chunk: a magnifying map shows in every row
-                const unsigned mine = ((actm >> u) & 1u) ? pk[u] : 0u;
-                const unsigned next = __shfl_down_sync(0xffffffffu, mine, 1);
-                unsigned m = __ballot_sync(0xffffffffu, (lane < 31) & (mine != 0u) & (next + 1u == mine));
-                int run = 1;
-                while (m) { m &= m >> 1; ++run; }
-                xrun = max(xrun, run);
-            }
-            dens = __reduce_max_sync(0xffffffffu, yrun) * xrun;
-        }
+        // mass.  Where the map collapses (a fold of the displacement field; affine magnification is excluded on the
+        // host, edf_fast_try_launch) that many voxels of one chunk can land on one cell and the accumulator would
+        // wrap.  The chunk's active voxels are counted against the window starts its box can hold; a chunk with
+        // more than EDF_SW_DENSE_MAX voxels per start cell on average scatters straight to dX in float instead.
+#ifndef EDF_SW_NO_GUARD
+        const int nact = __reduce_add_sync(0xffffffffu, __popc(actm));
+#else
+        const int nact = 0;
+#endif
         if (lane == 0 && mnz != INT_MAX) {
             int* b = s.bb[par];
             atomicMin(b + 0, mnz); atomicMin(b + 1, mny); atomicMin(b + 2, mnx);
             atomicMax(b + 3, mxz); atomicMax(b + 4, mxy); atomicMax(b + 5, mxx);
             atomicMax(b + 6, gbits);
-            atomicMax(b + 7, dens);
+            atomicAdd(b + 7, nact);
         }
         __syncthreads();                                           // box complete; previous chunk's flush done
-        if (tid < 8) s.bb[par == 0 ? 2 : par - 1][tid] = (tid < 3) ? INT_MAX : INT_MIN;
+        if (tid < 8) s.bb[par == 0 ? 2 : par - 1][tid] = (tid < 3) ? INT_MAX : (tid == 7 ? 0 : INT_MIN);
 #pragma unroll
         for (int u = 0; u < EDF_SW_MR; ++u) {
             const int yn = yc0 + EDF_SW_MR + u;
@@ -776,7 +758,8 @@ edf_swin3d_grad_kernel(const __grid_constant__ EdfParams p, const __grid_constan
         const int nzw = s.bb[par][3] - wz0 + NT, nyw = s.bb[par][4] - wy0 + NT;
         const int nq = ((s.bb[par][5] + NT - 1 - wx0) >> 2) + 1;
         const bool empty = s.bb[par][0] > s.bb[par][3];
-        const bool dense = s.bb[par][7] * EDF_SW_G > EDF_SW_DENSE_MAX;
+        const long long startcells = (long long)(s.bb[par][3] - wz0 + 1) * (s.bb[par][4] - wy0 + 1) * (s.bb[par][5] - s.bb[par][2] + 1);
+        const bool dense = !empty && (long long)s.bb[par][7] > EDF_SW_DENSE_MAX * startcells;
         const bool fit = !empty && !dense && nq <= EDF_SW_MAXQ && nzw <= EDF_SW_ROWS && nyw <= EDF_SW_ROWS && nzw * nyw <= EDF_SW_ROWS &&
                          !(L.input_mask >> 31);
         if (fit) {

@@ -16,6 +16,7 @@ PyTorch is used only for device memory, streams and copies.
 """
 import collections
 import ctypes
+import os
 import threading
 import warnings
 
@@ -247,13 +248,27 @@ def _host_tensor(x):
 _POOL_LOCK = threading.Lock()
 _POOL = {}                         # nbytes -> [uint8 pinned tensors]
 _POOL_FREE_BYTES = [0]
-_POOL_MAX_FREE_BYTES = 1 << 30
+# cap of the idle blocks kept per process (EDF_PINNED_POOL_MB; the default holds the results of a few 256^3
+# float32 calls -- DataLoader workers multiply it, so it is deliberately small)
+_POOL_MAX_FREE_BYTES = int(os.environ.get("EDF_PINNED_POOL_MB", "512")) << 20
 _POOL_MAX_PER_SIZE = 4
+# Blocks released by finalisers.  _PinnedLease.__del__ can run inside a cyclic-GC pass that starts while this very
+# thread holds _POOL_LOCK (any allocation under the lock can trigger one), so the finaliser takes NO lock: it appends
+# to a deque (atomic in CPython) and the next _pinned_result call files the blocks under the lock.
+_POOL_RETURNED = collections.deque()
 
 
 def _pool_release(tensor):
-    n = tensor.numel()
-    with _POOL_LOCK:
+    _POOL_RETURNED.append(tensor)
+
+
+def _pool_drain_locked():
+    while True:
+        try:
+            tensor = _POOL_RETURNED.popleft()
+        except IndexError:
+            return
+        n = tensor.numel()
         lst = _POOL.setdefault(n, [])
         if len(lst) < _POOL_MAX_PER_SIZE and _POOL_FREE_BYTES[0] + n <= _POOL_MAX_FREE_BYTES:
             lst.append(tensor)
@@ -286,6 +301,7 @@ def _pinned_result(shape, torch_dtype):
         return t, t.numpy()
     block = None
     with _POOL_LOCK:
+        _pool_drain_locked()
         lst = _POOL.get(n)
         if lst:
             block = lst.pop()
@@ -529,8 +545,8 @@ def _from_device(t, like):
     """Return the result in the same kind of container as the corresponding input."""
     if _is_tensor(like):
         return t if like.is_cuda else t.to(like.device)
-    # NumPy caller: device -> pinned host block from torch's caching host allocator (the block
-    # returns to the cache when the caller drops the array), so repeated calls copy at full
+    # NumPy caller: device -> pinned host block leased from this module's own recycled pool (the block
+    # returns to the pool when the caller drops the array), so repeated calls copy at full
     # PCIe speed without a fresh cudaHostAlloc each time.
     host, arr = _pinned_result(t.shape, t.dtype)
     host.copy_(t, non_blocking=True)

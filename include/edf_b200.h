@@ -117,6 +117,16 @@ int edf_deform_grid_grad(const edf_problem* problem, void* stream);
 int edf_deform_grid_batch(const edf_problem* problems, int32_t n, int32_t gradient,
                           void* stream);
 
+/* A batch whose problems differ only in their data: `n` volumes of one shape / dtype / order / mode / crop, each
+ * with its own input, output and displacement buffer and (optionally) its own affine map -- the data-augmentation
+ * loop of README.md:117-133 with the per-volume host work reduced to three pointers.  `proto` describes the common
+ * problem (ninputs == 1; its data pointers are ignored); in_ptrs / out_ptrs / disp_ptrs are `n` device addresses;
+ * `affines` holds n * naxis*(naxis+1) doubles (output->input maps, row-major) or is NULL (then proto->affine, if any,
+ * applies to every volume).  Same stream semantics as edf_deform_grid_batch. */
+int edf_deform_grid_batch_uniform(const edf_problem* proto, int32_t n, int32_t gradient,
+                                  const uint64_t* in_ptrs, const uint64_t* out_ptrs, const uint64_t* disp_ptrs,
+                                  const double* affines, void* stream);
+
 /* Mirror-boundary B-spline prefilter along one axis (orders 2..5; orders 0/1
  * copy), SciPy semantics: double line buffer, result cast to the output dtype.
  * Replaces scipy.ndimage.spline_filter1d at deform_grid.py:160/:168/:271.

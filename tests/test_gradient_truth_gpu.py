@@ -115,3 +115,36 @@ def test_gradient_under_magnification(edf, order):
     err_ref = float(np.abs(ref32.astype(np.float64) - ref).max())
     err_gpu = float(np.abs(gpu.astype(np.float64) - ref).max())
     assert err_gpu <= max(2e-5 * scale, 1.5 * err_ref), (err_gpu, err_ref, scale)
+
+
+@pytest.mark.parametrize("order", [0, 1, 3])
+def test_gradient_of_a_collapsing_field(edf, order):
+    """A displacement that pulls (almost) the whole volume onto a few voxels: thousands of output voxels per input
+    cell without any affine map -- the device-side density guard of the gradient windows (csrc/edf_swin.cuh,
+    edf_lean.cuh) must keep the fixed-point cells from wrapping.  Checked with and without the host-side steep hint."""
+    import importlib
+    dg = importlib.import_module("elasticdeform_b200.deform_grid")
+    shape = (48, 64, 64)
+    P = 5
+    D = np.zeros((3, P, P, P))
+    for h, n in enumerate(shape):
+        pos = np.linspace(0, n - 1, P)
+        sl = [None] * 3
+        sl[h] = slice(None)
+        D[h] = 0.97 * ((n - 1) / 2.0 - pos)[tuple(sl)]               # d(x) = 0.97 (centre - x): 3 % of the extent is left
+    G = np.ones(shape, np.float32)
+    kw = dict(order=order, prefilter=False)
+    truth = O.deform_grid_gradient(G.astype(np.float64), D, impl=_impl(), **kw)
+    ref32 = O.deform_grid_gradient(G, D, impl=_impl(), **kw)
+    scale = float(np.abs(truth).max())
+    assert scale > 1000.0
+    err_ref = float(np.abs(ref32.astype(np.float64) - truth).max())
+    saved = dg._steep_hint
+    for hint in (saved, lambda *a, **k: 0):
+        dg._steep_hint = hint
+        try:
+            gpu = edf.deform_grid_gradient(G, D, **kw)
+        finally:
+            dg._steep_hint = saved
+        err_gpu = float(np.abs(gpu.astype(np.float64) - truth).max())
+        assert err_gpu <= max(2e-5 * scale, 1.5 * err_ref), (err_gpu, err_ref, scale)
