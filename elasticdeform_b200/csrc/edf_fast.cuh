@@ -173,8 +173,8 @@ __device__ __forceinline__ void edf_fast_chunk_setup(EdfFastSmem<NAXIS>& s, int 
 // latency of this routine is on the critical path of every fast kernel (ncu, round 2: 400 warp-level calls of the
 // generic form -- a 64-iteration loop with local-memory index tables and a 13-way dtype switch per tap, ~10^5
 // cycles each -- accounted for a third of the stall samples of the order-0 forward kernel).  For float64 / float32
-// control points (what the fast kernels accept) the taps are fully unrolled: the loads are independent, the
-// products ((D * w_0) * w_1) * w_2 and the running sum keep the reference's order and rounding (no FMA).
+// control points (what the fast kernels accept) the taps run four at a time with independent loads and no dtype
+// switch; the products ((D * w_0) * w_1) * w_2 and the running sum keep the reference's order and rounding (no FMA).
 template <int NAXIS, typename TD>
 __device__ __forceinline__ void edf_displacement_exact_unrolled(const EdfParams& p, const int* o, double* dd)
 {
@@ -193,26 +193,31 @@ __device__ __forceinline__ void edf_displacement_exact_unrolled(const EdfParams&
             doff[a][l] = idx * p.dstr[a + 1];
         }
     }
+    // One row of four taps per iteration (independent loads), rows and components in rolled loops with the weight /
+    // offset tables in local memory: the routine must stay SMALL IN REGISTERS -- it is called from inside the voxel
+    // loops of the table kernels, and every register it uses is one the caller has to spill around the call (a fully
+    // unrolled form, 90 registers, cost edf_fast_real_kernel<3,3,double> 640 bytes of extra spills and half its speed).
 #pragma unroll 1
     for (int h = 0; h < NAXIS; ++h) {
         const char* bh = p.disp + p.dstr[0] * h;
         double sum = 0.0;
-        if (NAXIS == 3) {
+        constexpr int NROW = (NAXIS == 3) ? 16 : 4;
+#pragma unroll 1
+        for (int r = 0; r < NROW; ++r) {
+            const int i = (NAXIS == 3) ? (r >> 2) : 0, j = (NAXIS == 3) ? (r & 3) : r;
+            const char* row = (NAXIS == 3) ? bh + doff[0][i] + doff[1][j] : bh + doff[0][j];
+            const double wij = (NAXIS == 3) ? 0.0 : 0.0;
+            (void)wij;
+            double c[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                double c[16];
+            for (int k = 0; k < 4; ++k) c[k] = (double)*(const TD*)(row + doff[NAXIS - 1][k]);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) c[q] = (double)*(const TD*)(bh + doff[0][i] + doff[1][q >> 2] + doff[2][q & 3]);
-#pragma unroll
-                for (int q = 0; q < 16; ++q)
-                    sum = xadd(sum, xmul(xmul(xmul(c[q], dw[0][i]), dw[1][q >> 2]), dw[2][q & 3]));
+            for (int k = 0; k < 4; ++k) {
+                double t = c[k];
+                if (NAXIS == 3) t = xmul(xmul(xmul(t, dw[0][i]), dw[1][j]), dw[2][k]);
+                else            t = xmul(xmul(t, dw[0][j]), dw[1][k]);
+                sum = xadd(sum, t);
             }
-        } else {
-            double c[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) c[q] = (double)*(const TD*)(bh + doff[0][q >> 2] + doff[1][q & 3]);
-#pragma unroll
-            for (int q = 0; q < 16; ++q) sum = xadd(sum, xmul(xmul(c[q], dw[0][q >> 2]), dw[1][q & 3]));
         }
         dd[h] = sum;
     }
