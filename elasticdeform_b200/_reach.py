@@ -23,6 +23,7 @@ one cached matrix per (P, r) and the whole bound is naxis small matrix products.
 import numpy
 
 _MATRIX_CACHE = {}
+_MATRIX_LOCK = __import__('threading').Lock()
 _MAX_FINE = 1 << 18                 # cap of the refined coefficient count (levels are lowered to fit)
 
 
@@ -40,7 +41,8 @@ def refine_matrix(P, r):
     """(n_fine, P) matrix taking P control coefficients to the level-r refined coefficients with
     indices -1 .. 2^r * P + 1 (units of 2^-r control spacings), mirror extension included."""
     key = (int(P), int(r))
-    M = _MATRIX_CACHE.get(key)
+    with _MATRIX_LOCK:
+        M = _MATRIX_CACHE.get(key)
     if M is None:
         idx = numpy.arange(-1, P + 2)
         if P > 1:
@@ -52,9 +54,10 @@ def refine_matrix(P, r):
         M = numpy.eye(P)[m]
         for _ in range(r):
             M = _refine_rows(M)
-        if len(_MATRIX_CACHE) > 64:
-            _MATRIX_CACHE.clear()
-        _MATRIX_CACHE[key] = M
+        with _MATRIX_LOCK:
+            if len(_MATRIX_CACHE) > 64:
+                _MATRIX_CACHE.clear()
+            _MATRIX_CACHE[key] = M
     return M
 
 

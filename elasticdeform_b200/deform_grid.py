@@ -319,15 +319,35 @@ def _pinned_result(shape, torch_dtype):
 
 
 _SIDE_STREAMS = {}
+_CACHE_LOCK = threading.Lock()                 # guards the module-level caches below (multi-threaded callers)
+
+
+def _drain_on_error(fn):
+    """The slab pipelines queue copies on side streams into device buffers and leased pinned blocks.  If anything
+    raises in the middle (a launch failure, MemoryError from the line filter), those buffers go back to the
+    caching allocator / the pinned pool while copies may still be in flight: wait for the device first."""
+    def wrapper(lib, device, *args, **kwargs):
+        try:
+            return fn(lib, device, *args, **kwargs)
+        except BaseException:
+            try:
+                torch.cuda.synchronize(device)
+            except Exception:
+                pass
+            raise
+    wrapper.__name__ = fn.__name__
+    wrapper.__doc__ = fn.__doc__
+    return wrapper
 
 
 def _side_streams(device):
     """The upload / download streams of the slab pipeline, one pair per device (creating a stream per
     call costs more than the enqueue of a slab)."""
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-    pair = _SIDE_STREAMS.get(key)
-    if pair is None:
-        pair = _SIDE_STREAMS[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+    with _CACHE_LOCK:
+        pair = _SIDE_STREAMS.get(key)
+        if pair is None:
+            pair = _SIDE_STREAMS[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
     return pair
 
 
@@ -352,14 +372,16 @@ def _slab_reach(displacement_f, order, dim0, off0, slabs):
     to the host)."""
     c0 = displacement_f[0].to('cpu', torch.float64).numpy()
     key = (c0.tobytes(), c0.shape, int(dim0), int(off0), tuple(slabs))
-    b = _BOUNDS_CACHE.get(key)
+    with _CACHE_LOCK:
+        b = _BOUNDS_CACHE.get(key)
     if b is None:
         b = _reach.slab_bounds(c0, dim0, off0, slabs)
         if b is None:
             return None
-        _BOUNDS_CACHE[key] = b
-        while len(_BOUNDS_CACHE) > 8:
-            _BOUNDS_CACHE.popitem(last=False)
+        with _CACHE_LOCK:
+            _BOUNDS_CACHE[key] = b
+            while len(_BOUNDS_CACHE) > 8:
+                _BOUNDS_CACHE.popitem(last=False)
     return _reach.integer_reach(b, max(order))
 
 
@@ -388,6 +410,7 @@ class _SlabLauncher(object):
         _lib.check(self.fn(self.ref, self.stream))
 
 
+@_drain_on_error
 def _pipelined_forward(lib, device, Xs, displacement, output_shapes, output_offset, axis, order, mode, cval,
                        h, flags, prefilter=False):
     pf = [int(order[i]) if (prefilter and order[i] > 1) else 0 for i in range(len(Xs))]
@@ -458,6 +481,7 @@ def _pipelined_forward(lib, device, Xs, displacement, output_shapes, output_offs
     return [p[1] for p in Y_hn]
 
 
+@_drain_on_error
 def _pipelined_gradient(lib, device, dYs, X_shape, displacement, output_offset, axis, order, mode, cval,
                         h, flags, prefilter=False):
     pf = [int(order[i]) if (prefilter and order[i] > 1) else 0 for i in range(len(dYs))]
