@@ -313,21 +313,40 @@ edf_line_filter_kernel(const __grid_constant__ EdfLineParams p)
     const int n = (int)p.n, ld = p.ld;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const bool f32 = p.in_dtype == EDF_F32, f64 = p.in_dtype == EDF_F64;
+    // (EDF_LINE_UNROLL independent global loads per thread before the first dependent conversion / store: with one
+    //  load in flight per warp the staging ran at DRAM latency -- 35 % of the kernel's stall samples sat on the
+    //  conversion of the loaded value)
+    constexpr int UN = 8;
     if (p.line_fastest) {
         for (int l = warp; l < nl; l += nwarps) {
             const char* src = p.in + in_off[l];
             double* dst = sbuf + (size_t)l * ld;
-            for (int i = lane; i < n; i += 32) {
-                const char* q = src + (int64_t)i * p.in_lstr;
-                dst[i] = f32 ? (double)*(const float*)q : (f64 ? *(const double*)q : edf_load(q, p.in_dtype));
+            for (int i0 = lane; i0 < n; i0 += 32 * UN) {
+                double v[UN];
+#pragma unroll
+                for (int k = 0; k < UN; ++k) {
+                    const int i = i0 + 32 * k;
+                    const char* q = src + (int64_t)min(i, n - 1) * p.in_lstr;
+                    v[k] = f32 ? (double)*(const float*)q : (f64 ? *(const double*)q : edf_load(q, p.in_dtype));
+                }
+#pragma unroll
+                for (int k = 0; k < UN; ++k)
+                    if (i0 + 32 * k < n) dst[i0 + 32 * k] = v[k];
             }
         }
     } else {
-        for (int i = warp; i < n; i += nwarps) {
-            const int64_t io = (int64_t)i * p.in_lstr;
+        for (int i0 = warp * UN; i0 < n; i0 += nwarps * UN) {
             for (int l = lane; l < nl; l += 32) {
-                const char* q = p.in + in_off[l] + io;
-                sbuf[(size_t)l * ld + i] = f32 ? (double)*(const float*)q : (f64 ? *(const double*)q : edf_load(q, p.in_dtype));
+                const char* base = p.in + in_off[l];
+                double v[UN];
+#pragma unroll
+                for (int k = 0; k < UN; ++k) {
+                    const char* q = base + (int64_t)min(i0 + k, n - 1) * p.in_lstr;
+                    v[k] = f32 ? (double)*(const float*)q : (f64 ? *(const double*)q : edf_load(q, p.in_dtype));
+                }
+#pragma unroll
+                for (int k = 0; k < UN; ++k)
+                    if (i0 + k < n) sbuf[(size_t)l * ld + i0 + k] = v[k];
             }
         }
     }

@@ -18,6 +18,13 @@ struct EdfLineFilter {
     int32_t trunc_max[2];     // K4 only: ceil(log(1e-15)/log|z|)   (deform.c:1119)
 };
 
+// Both recursions run on blocks of EDF_LINE_BLK elements held in registers: the loads of a block are independent of
+// the recursion (issued together, ahead of it), the stores follow it, so that the dependent chain per element is
+// the one or two fp64 operations of the filter itself and not a shared-memory round trip (the line lives in shared
+// memory; a load after a store to the same array cannot be hoisted by the compiler).  Operation order and rounding per
+// element are unchanged -- same results bit for bit.
+#define EDF_LINE_BLK 8
+
 // K3: in-place on a contiguous double line c[0..n)
 EDF_HD void edf_prefilter_line(double* c, int64_t n, const EdfLineFilter& f)
 {
@@ -29,15 +36,54 @@ EDF_HD void edf_prefilter_line(double* c, int64_t n, const EdfLineFilter& f)
         // causal initialisation, mirror boundary (exact finite sum)
         double c0 = xadd(c[0], xmul(zn1, c[n - 1]));
         double zi = z;
-        for (int64_t i = 1; i < n - 1; ++i) {
-            c0 = xadd(c0, xmul(zi, xadd(c[i], xmul(zn1, c[n - 1 - i]))));
-            zi = xmul(zi, z);
+        {
+            int64_t i = 1;
+            for (; i + EDF_LINE_BLK <= n - 1; i += EDF_LINE_BLK) {
+                double a[EDF_LINE_BLK], b[EDF_LINE_BLK];
+#pragma unroll
+                for (int k = 0; k < EDF_LINE_BLK; ++k) { a[k] = c[i + k]; b[k] = c[n - 1 - i - k]; }
+#pragma unroll
+                for (int k = 0; k < EDF_LINE_BLK; ++k) {
+                    c0 = xadd(c0, xmul(zi, xadd(a[k], xmul(zn1, b[k]))));
+                    zi = xmul(zi, z);
+                }
+            }
+            for (; i < n - 1; ++i) {
+                c0 = xadd(c0, xmul(zi, xadd(c[i], xmul(zn1, c[n - 1 - i]))));
+                zi = xmul(zi, z);
+            }
         }
         c[0] = xdiv(c0, xsub(1.0, xmul(zn1, zn1)));
-        for (int64_t i = 1; i < n; ++i) c[i] = xadd(c[i], xmul(z, c[i - 1]));
+        {
+            double prev = c[0];
+            int64_t i = 1;
+            for (; i + EDF_LINE_BLK <= n; i += EDF_LINE_BLK) {
+                double a[EDF_LINE_BLK];
+#pragma unroll
+                for (int k = 0; k < EDF_LINE_BLK; ++k) a[k] = c[i + k];
+#pragma unroll
+                for (int k = 0; k < EDF_LINE_BLK; ++k) { prev = xadd(a[k], xmul(z, prev)); a[k] = prev; }
+#pragma unroll
+                for (int k = 0; k < EDF_LINE_BLK; ++k) c[i + k] = a[k];
+            }
+            for (; i < n; ++i) { prev = xadd(c[i], xmul(z, prev)); c[i] = prev; }
+        }
         // anti-causal initialisation, mirror boundary
         c[n - 1] = xdiv(xmul(xadd(xmul(z, c[n - 2]), c[n - 1]), z), xsub(xmul(z, z), 1.0));
-        for (int64_t i = n - 2; i >= 0; --i) c[i] = xmul(z, xsub(c[i + 1], c[i]));
+        {
+            double next = c[n - 1];
+            int64_t i = n - 2;
+            for (; i - (EDF_LINE_BLK - 1) >= 0; i -= EDF_LINE_BLK) {
+                double a[EDF_LINE_BLK];
+#pragma unroll
+                for (int k = 0; k < EDF_LINE_BLK; ++k) a[k] = c[i - k];
+#pragma unroll
+                for (int k = 0; k < EDF_LINE_BLK; ++k) { next = xmul(z, xsub(next, a[k])); a[k] = next; }
+#pragma unroll
+                for (int k = 0; k < EDF_LINE_BLK; ++k) c[i - k] = a[k];
+            }
+            for (; i >= 0; --i) { next = xmul(z, xsub(next, c[i])); c[i] = next; }
+        }
     }
 }
 
@@ -48,19 +94,53 @@ EDF_HD void edf_prefilter_adjoint_line(double* ln, int64_t n, const EdfLineFilte
     for (int h = 0; h < f.npoles; ++h) {
         const double p = f.pole[h];
         double sum = xmul(p, ln[0]);
-        ln[0] = xmul(-p, ln[0]);
-        for (int64_t l = 1; l < n - 1; ++l) {
-            sum = xmul(p, xadd(sum, ln[l]));
-            ln[l] = xmul(p, xsub(ln[l - 1], ln[l]));
+        {
+            // ln[l] = p * (ln[l-1] - ln[l]) reads the UPDATED ln[l-1] (in-place loop, deform.c:1123-1126): carried in a register
+            double before = xmul(-p, ln[0]);
+            ln[0] = before;
+            int64_t l = 1;
+            for (; l + EDF_LINE_BLK <= n - 1; l += EDF_LINE_BLK) {
+                double a[EDF_LINE_BLK];
+#pragma unroll
+                for (int k = 0; k < EDF_LINE_BLK; ++k) a[k] = ln[l + k];
+#pragma unroll
+                for (int k = 0; k < EDF_LINE_BLK; ++k) {
+                    sum = xmul(p, xadd(sum, a[k]));
+                    before = xmul(p, xsub(before, a[k]));
+                    a[k] = before;
+                }
+#pragma unroll
+                for (int k = 0; k < EDF_LINE_BLK; ++k) ln[l + k] = a[k];
+            }
+            for (; l < n - 1; ++l) {
+                const double cur = ln[l];
+                sum = xmul(p, xadd(sum, cur));
+                before = xmul(p, xsub(before, cur));
+                ln[l] = before;
+            }
         }
         sum = xmul(xdiv(p, xsub(xmul(p, p), 1.0)), xadd(sum, ln[n - 1]));
         ln[n - 2] = xadd(ln[n - 2], xmul(p, sum));
         ln[n - 1] = sum;
-        for (int64_t l = n - 2; l >= 0; --l) ln[l] = xadd(ln[l], xmul(p, ln[l + 1]));
+        {
+            double next = ln[n - 1];
+            int64_t l = n - 2;
+            for (; l - (EDF_LINE_BLK - 1) >= 0; l -= EDF_LINE_BLK) {
+                double a[EDF_LINE_BLK];
+#pragma unroll
+                for (int k = 0; k < EDF_LINE_BLK; ++k) a[k] = ln[l - k];
+#pragma unroll
+                for (int k = 0; k < EDF_LINE_BLK; ++k) { next = xadd(a[k], xmul(p, next)); a[k] = next; }
+#pragma unroll
+                for (int k = 0; k < EDF_LINE_BLK; ++k) ln[l - k] = a[k];
+            }
+            for (; l >= 0; --l) { next = xadd(ln[l], xmul(p, next)); ln[l] = next; }
+        }
         if ((int64_t)f.trunc_max[h] < n) {
             double zn = p;
+            const double l0 = ln[0];
             for (int64_t l = 1; l < n; ++l) {
-                ln[l] = xadd(ln[l], xmul(zn, ln[0]));
+                ln[l] = xadd(ln[l], xmul(zn, l0));
                 zn = xmul(zn, p);
             }
         } else {
@@ -70,8 +150,9 @@ EDF_HD void edf_prefilter_adjoint_line(double* ln, int64_t n, const EdfLineFilte
             ln[0] = xdiv(ln[0], xsub(1.0, xmul(z2n, z2n)));
             ln[n - 1] = xadd(ln[n - 1], xmul(z2n, ln[0]));
             z2n = xmul(z2n, xmul(z2n, iz));
+            const double l0 = ln[0];
             for (int64_t l = 1; l <= n - 2; ++l) {
-                ln[l] = xadd(ln[l], xmul(xadd(zn, z2n), ln[0]));
+                ln[l] = xadd(ln[l], xmul(xadd(zn, z2n), l0));
                 zn = xmul(zn, p);
                 z2n = xmul(z2n, iz);
             }

@@ -103,3 +103,25 @@ def test_line_filters_device_code():
             c = np.zeros_like(x)
             hs.spline_filter1d_grad(x, c, 0, order)
             np.testing.assert_array_equal(c, O.spline_filter1d_grad(x, 0, order, impl="port"))
+
+
+def test_line_filters_bit_exact_all_lengths():
+    """The register-blocked line recursions of csrc/edf_spline_lines.h (blocks of 8 elements, remainders, lines shorter
+    than a block): K3 == scipy.ndimage.spline_filter1d and K4 == the reference's spline_filter1d_grad bit for bit."""
+    import scipy.ndimage
+    H = hostsim.HostSimModule()
+    mod, _ = O._backend("ref" if O.ref_available() else "port")
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 5, 8, 9, 10, 17, 18, 25, 31, 64, 100, 257):
+        for order in (2, 3, 4, 5):
+            for dt in (np.float64, np.float32):
+                X = rng.random((3, n, 4)).astype(dt)
+                out = np.zeros_like(X)
+                H.spline_filter1d(X, 1, order, out)
+                ref = scipy.ndimage.spline_filter1d(X, order=order, axis=1, output=dt, mode="mirror")
+                np.testing.assert_array_equal(out, ref, err_msg="K3 n=%d order=%d" % (n, order))
+                out2 = np.zeros_like(X)
+                H.spline_filter1d_grad(X, out2, 1, order)
+                ref2 = np.zeros_like(X)
+                mod.spline_filter1d_grad(X, ref2, 1, order)
+                np.testing.assert_array_equal(out2, ref2, err_msg="K4 n=%d order=%d" % (n, order))
