@@ -62,6 +62,7 @@ struct EdfSwinSmem {
     int    sx[EDF_SW_TX];
     int    ny, nx, nonzero, pad_;
     int    bb[3][8];                // [chunk % 3]: min z,y,x start, max z,y,x start of the chunk's active voxels
+    int    hb[2][8];                // gradient: the same per 2-row half, only when the full box does not fit the window
     unsigned long long mbar;        // transaction barrier of the TMA bulk copies that fill the window
     double A[3][EDF_SW_G][EDF_SW_NC][EDF_SW_NC];
     double Bw[EDF_SW_G][3][EDF_SW_MR][EDF_SW_NC];
@@ -632,6 +633,7 @@ edf_swin3d_grad_kernel(const __grid_constant__ EdfParams p, const __grid_constan
     // ---- prologue: control tables, z-contraction A, empty boxes, zero window
     if (tid == 0) s.nonzero = 0;
     if (tid < 3 * 8) (&s.bb[0][0])[tid] = ((tid & 7) < 3) ? INT_MAX : ((tid & 7) == 7 ? 0 : INT_MIN);
+    if (tid >= 32 && tid < 48) (&s.hb[0][0])[tid - 32] = ((tid & 7) < 3) ? INT_MAX : INT_MIN;
     if (tid < EDF_SW_TX) {
         edf_fast_ctrl_entry(p, 2, min((int64_t)(x0 + tid), p.odim[2] - 1), s.wx[tid], &s.sx[tid]);
     } else if (tid < EDF_SW_TX + EDF_SW_RY) {
@@ -754,14 +756,51 @@ edf_swin3d_grad_kernel(const __grid_constant__ EdfParams p, const __grid_constan
             const int yn = yc0 + EDF_SW_MR + u;
             gvn[u] = (tok && c + 1 < nchunk && yn < ody) ? __ldg(pdy + (obase_zx + yn * osy)) : 0.f;
         }
-        const int wz0 = s.bb[par][0], wy0 = s.bb[par][1], wx0 = s.bb[par][2] & ~3;
-        const int nzw = s.bb[par][3] - wz0 + NT, nyw = s.bb[par][4] - wy0 + NT;
-        const int nq = ((s.bb[par][5] + NT - 1 - wx0) >> 2) + 1;
         const bool empty = s.bb[par][0] > s.bb[par][3];
-        const long long startcells = (long long)(s.bb[par][3] - wz0 + 1) * (s.bb[par][4] - wy0 + 1) * (s.bb[par][5] - s.bb[par][2] + 1);
+        const long long startcells = (long long)(s.bb[par][3] - s.bb[par][0] + 1) * (s.bb[par][4] - s.bb[par][1] + 1) * (s.bb[par][5] - s.bb[par][2] + 1);
         const bool dense = !empty && (long long)s.bb[par][7] > EDF_SW_DENSE_MAX * startcells;
-        const bool fit = !empty && !dense && nq <= EDF_SW_MAXQ && nzw <= EDF_SW_ROWS && nyw <= EDF_SW_ROWS && nzw * nyw <= EDF_SW_ROWS &&
-                         !(L.input_mask >> 31);
+        const bool usewin = !empty && !dense && !(L.input_mask >> 31);
+        bool fitfull;
+        {
+            const int nzw_ = s.bb[par][3] - s.bb[par][0] + NT, nyw_ = s.bb[par][4] - s.bb[par][1] + NT;
+            const int nq_ = ((s.bb[par][5] + NT - 1 - (s.bb[par][2] & ~3)) >> 2) + 1;
+            fitfull = nq_ <= EDF_SW_MAXQ && nzw_ <= EDF_SW_ROWS && nyw_ <= EDF_SW_ROWS && nzw_ * nyw_ <= EDF_SW_ROWS;
+        }
+        // A chunk whose box outgrows the window (a stretch of steep field: ~5 % of the chunks of the headline volume) is
+        // scattered as two 2-row halves, each through its own box, before anything falls back to float atomics on dX
+        // (which cost ~5x the window path per voxel).
+        const int npass = (usewin && !fitfull) ? 2 : 1;
+        if (npass == 2) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                int hn0 = INT_MAX, hn1 = INT_MAX, hn2 = INT_MAX, hx0 = INT_MIN, hx1 = INT_MIN, hx2 = INT_MIN;
+#pragma unroll
+                for (int u = 2 * hf; u < 2 * hf + 2; ++u)
+                    if ((actm >> u) & 1u) {
+                        const int stz = z - EDF_SW_PK_BIAS + (int)(pk[u] >> 20), sty = yc0 + u - EDF_SW_PK_BIAS + (int)((pk[u] >> 10) & 1023u);
+                        const int stx = x - EDF_SW_PK_BIAS + (int)(pk[u] & 1023u);
+                        hn0 = min(hn0, stz); hn1 = min(hn1, sty); hn2 = min(hn2, stx);
+                        hx0 = max(hx0, stz); hx1 = max(hx1, sty); hx2 = max(hx2, stx);
+                    }
+                hn0 = __reduce_min_sync(0xffffffffu, hn0); hn1 = __reduce_min_sync(0xffffffffu, hn1); hn2 = __reduce_min_sync(0xffffffffu, hn2);
+                hx0 = __reduce_max_sync(0xffffffffu, hx0); hx1 = __reduce_max_sync(0xffffffffu, hx1); hx2 = __reduce_max_sync(0xffffffffu, hx2);
+                if (lane == 0 && hn0 != INT_MAX) {
+                    int* hbp = s.hb[hf];
+                    atomicMin(hbp + 0, hn0); atomicMin(hbp + 1, hn1); atomicMin(hbp + 2, hn2);
+                    atomicMax(hbp + 3, hx0); atomicMax(hbp + 4, hx1); atomicMax(hbp + 5, hx2);
+                }
+            }
+            __syncthreads();
+        }
+        for (int ps = 0; ps < npass; ++ps) {
+        const int* bx_ = (npass == 2) ? s.hb[ps] : s.bb[par];
+        const unsigned rowmask = (npass == 2) ? (ps ? 0xcu : 0x3u) : 0xfu;
+        const int wz0 = bx_[0], wy0 = bx_[1], wx0 = bx_[2] & ~3;
+        const int nzw = bx_[3] - wz0 + NT, nyw = bx_[4] - wy0 + NT;
+        const int nq = ((bx_[5] + NT - 1 - wx0) >> 2) + 1;
+        const bool pempty = bx_[0] > bx_[3];
+        const bool fit = usewin && !pempty && nq <= EDF_SW_MAXQ && nzw <= EDF_SW_ROWS && nyw <= EDF_SW_ROWS && nzw * nyw <= EDF_SW_ROWS;
+        if (ps) __syncthreads();                                   // the first half's flush has re-zeroed the window
         if (fit) {
             // fixed-point scale: the largest possible contribution, max|dY| of the chunk times the largest weight
             // product of this order, maps to just under 2^22 -- the range of the magic-number rounding that
@@ -780,7 +819,7 @@ edf_swin3d_grad_kernel(const __grid_constant__ EdfParams p, const __grid_constan
                              (x - EDF_SW_PK_BIAS - wx0);
 #pragma unroll
             for (int u = 0; u < EDF_SW_MR; ++u) {
-                if (!((actm >> u) & 1u)) continue;
+                if (!(((actm & rowmask) >> u) & 1u)) continue;
                 const int rz = (int)(pk[u] >> 20), ryw = (int)((pk[u] >> 10) & 1023u), rx = (int)(pk[u] & 1023u);
                 int* b0 = win + (lin0 + u * EDF_SW_PITCH + (rz * nyw + ryw) * EDF_SW_PITCH + rx);
                 float wzf[NT], wyf[NT], wxf[NT];
@@ -855,8 +894,13 @@ edf_swin3d_grad_kernel(const __grid_constant__ EdfParams p, const __grid_constan
                     }
                 }
             }
-        } else if (!empty) {
-            dirm |= actm;                                          // does not fit the window (very steep field)
+        } else if (!pempty) {
+            dirm |= actm & rowmask;                                // does not fit the window (very steep field)
+        }
+        }
+        if (npass == 2) {
+            __syncthreads();                                       // half boxes read by every thread: reset for the next user
+            if (tid < 16) (&s.hb[0][0])[tid] = ((tid & 7) < 3) ? INT_MAX : INT_MIN;
         }
         // ---- voxels that bypass the window: direct global atomics in float
         if (dirm) {

@@ -180,7 +180,7 @@ def _launch(lib, gradient, ins, outs, displacement_f, output_offset, axis, order
 # download still overlaps them and the kernels.  Line filters are independent per line: the results
 # are bit-identical to the one-shot path.
 _PIPELINE_MIN_BYTES = 16 << 20
-_PIPELINE_SLABS = 8
+_PIPELINE_SLABS = int(os.environ.get("EDF_PIPELINE_SLABS", "8"))   # slabs per call (8 measured best on B200: scripts/e2e_slabs.py)
 
 
 def _pipeline_plan(Xs, axis, order, mode, prefilter, inverse_affine, in_dim0, out_dim0, gradient):
