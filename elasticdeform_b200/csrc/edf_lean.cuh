@@ -707,9 +707,9 @@ __device__ __noinline__ void edf_gradwin_slow_voxel(const EdfParams& p, const Ed
 
 // FLUSH: 0 = scalar atomics, 1 = 16-byte vector atomics, 2 = TMA bulk reduce-add per window row
 // (cp.reduce.async.bulk ... .add.f32, SASS UBLKRED).  A single tensor-map reduce of the whole box
-// (cp.reduce.async.bulk.tensor.3d, UTMAREDG) would be the natural form, but every tensor-map TMA
-// instruction traps with cudaErrorIllegalInstruction on this pool's B200 boxes, also in the
-// stand-alone reproducer scripts/experiments/tma_reduce_test.cu, so the row form is used.
+// (cp.reduce.async.bulk.tensor.3d, UTMAREDG) would be the natural form; it needs the window converted to
+// float in place and a 16-byte aligned innermost box coordinate (round 1 took the traps of unaligned
+// coordinates for a defect of the pool: scripts/experiments/tma_tensor_test.cu, DESIGN.md "TMA").
 template <int ORDER, int FLUSH>
 __global__ void __launch_bounds__(EDF_GW_THREADS, EDF_GW_MINB)
 edf_lean3d_gradwin_kernel(const __grid_constant__ EdfParams p, const __grid_constant__ EdfFastLaunch L, const int ii)

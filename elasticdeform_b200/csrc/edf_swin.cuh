@@ -79,8 +79,9 @@ __device__ __forceinline__ void edf_cp_async4(uint32_t smem_dst, const float* gs
 }
 
 // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP): one instruction moves a whole window row global -> shared and
-//      reports its bytes to a transaction mbarrier.  (The tensor-map forms of TMA trap on this pool's B200 boxes,
-//      see DESIGN.md; the row form needs no descriptor and suits the data-dependent box anyway.)
+//      reports its bytes to a transaction mbarrier.  (The tensor-map form -- UTMALDG boxes, edf_tile.cuh -- was
+//      measured 17 % slower in this kernel structure; the row form needs no descriptor and suits the
+//      data-dependent box.)
 #ifndef EDF_SW_BULK
 #define EDF_SW_BULK 1              // 1: stage the window with TMA bulk copies; 0: with 16-byte cp.async (LDGSTS)
 #endif
