@@ -114,6 +114,16 @@ def deform_grid_batch(Xs, displacements, order=3, mode='constant', cval=0.0, cro
         return [_dg._from_device(o, x) for o, x in zip(outs, Xs)]
 
 
+def inverse_affines_stacked(affines, axis):
+    """(nb, n, n + 1) inverse (output -> input) maps of a batch of forward affine maps in one vectorised inversion;
+    row b equals ``_compute_inverse_affine(_normalize_affine(affines[b], axis))`` (reference deform_grid.py:382-399)."""
+    naxis = len(axis[0])
+    A = numpy.stack([_dg._normalize_affine(a, axis) for a in affines])              # (nb, n, n + 1)
+    Ainv = numpy.linalg.inv(A[:, :, :naxis])
+    inv_all = numpy.concatenate([Ainv, -numpy.einsum('bij,bj->bi', Ainv, A[:, :, naxis])[:, :, None]], axis=2)
+    return numpy.ascontiguousarray(inv_all, dtype='float64')
+
+
 def _uniform_batch(lib, device, Xs, d_all, order, mode, cval, crop, affines, gradient, X_shape, flags):
     """Volumes of one shape and dtype without a per-volume prefilter: ONE edf_problem describes the batch and the
     C-ABI receives three arrays of device addresses (edf_deform_grid_batch_uniform); the per-volume Python work is
@@ -134,12 +144,7 @@ def _uniform_batch(lib, device, Xs, d_all, order, mode, cval, crop, affines, gra
     cv = _dg._normalize_cval(cval, X0)
     naxis = len(axis[0])
     # inverse affine maps of the whole batch in one vectorised inversion
-    inv_all = None
-    if affines is not None:
-        A = numpy.stack([_dg._normalize_affine(a, axis) for a in affines])          # (nb, n, n + 1)
-        Ainv = numpy.linalg.inv(A[:, :, :naxis])
-        inv_all = numpy.concatenate([Ainv, -numpy.einsum('bij,bj->bi', Ainv, A[:, :, naxis])[:, :, None]], axis=2)
-        inv_all = numpy.ascontiguousarray(inv_all, dtype='float64')
+    inv_all = None if affines is None else inverse_affines_stacked(affines, axis)
     xs = [_dg._to_device(x, device) for x in Xs]
     if not all(x.stride() == xs[0].stride() for x in xs):
         return None

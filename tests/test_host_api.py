@@ -190,3 +190,26 @@ def test_torch_wrapper_plumbing_without_gpu(monkeypatch):
     assert torch.equal(a.grad, torch.full((4, 5), 2.0)) and torch.equal(b.grad, torch.full((4, 5), 6.0, dtype=torch.float64))
     res = etorch.ElasticDeform.apply(torch.as_tensor(D), (), {}, a)        # the Function itself: always a tuple
     assert isinstance(res, tuple) and len(res) == 1
+
+
+def test_batch_inverse_affines_match_per_volume_inversion():
+    """The uniform batch entry inverts all affine maps of a batch at once: same numbers as the per-volume helper."""
+    import importlib
+    from elasticdeform_b200 import batch
+    dg = importlib.import_module("elasticdeform_b200.deform_grid")
+    rng = np.random.default_rng(9)
+    for n in (2, 3):
+        axis = [tuple(range(n))]
+        As = []
+        for b in range(6):
+            M = np.eye(n) + 0.2 * rng.standard_normal((n, n))
+            t = rng.standard_normal(n) * 10
+            A = np.concatenate([M, t[:, None]], axis=1)
+            # 2-D also in the homogeneous (3, 3) form the reference accepts (its check of the last row is written for
+            # 2-D: deform_grid.py:387; a (4, 4) matrix fails it there, and here)
+            As.append(np.vstack([A, [0, 0, 1]]) if (n == 2 and b % 2) else A)
+        inv = batch.inverse_affines_stacked(As, axis)
+        assert inv.shape == (6, n, n + 1) and inv.dtype == np.float64 and inv.flags.c_contiguous
+        for b, A in enumerate(As):
+            one = dg._compute_inverse_affine(dg._normalize_affine(np.asarray(A), axis))
+            np.testing.assert_allclose(inv[b], one, rtol=1e-13, atol=1e-13)
